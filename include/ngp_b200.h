@@ -1,0 +1,167 @@
+/* ngp_b200.h -- C ABI of the B200-native (sm_100a) hot path of kwea123/ngp_pl.
+ *
+ * This is the drop-in boundary. The reference's native surface for this path is the pybind11 module
+ * `vren` (reference models/csrc/binding.cpp:234-250, prototypes in models/csrc/include/utils.h:9-126)
+ * plus the tinycudann modules its models/networks.py:36-77 instantiates. Each entry point below names
+ * the reference interface it replaces. Conventions:
+ *   - plain device pointers + sizes; no torch types; the CALLER owns and allocates every buffer
+ *     (workspace sizes are queried with the *_workspace functions);
+ *   - `stream` is a cudaStream_t passed as void*; every launch is asynchronous on that stream;
+ *   - return 0 on success, a cudaError_t (>0) on a CUDA failure, NGP_EINVAL (-22) on a bad argument;
+ *   - all tensors are dense row-major ("contiguous" in the reference's CHECK_INPUT sense).
+ */
+#ifndef NGP_B200_H
+#define NGP_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NGP_MAX_LEVELS 16
+#define NGP_ABI_VERSION 1
+
+int ngp_abi_version(void);
+
+/* ----------------------------------------------------------------------------------------------
+ * The twelve vren operators
+ * -------------------------------------------------------------------------------------------- */
+
+/* vren.ray_aabb_intersect (binding.cpp:4-16, intersection.cu:25-100). hits_t (n_rays,max_hits,2) and
+ * hits_voxel_idx (n_rays,max_hits) are filled with -1 then written in hit order; hit_cnt (n_rays).
+ * The reference sorts hits by t1 afterwards with torch ops; the Python shim does the same when
+ * max_hits > 1 (the hot path uses n_voxels = max_hits = 1, where the sort is the identity). */
+int ngp_ray_aabb_intersect(const float* rays_o, const float* rays_d, const float* centers, const float* half_sizes,
+                           int n_rays, int n_voxels, int max_hits, int* hit_cnt, float* hits_t,
+                           int64_t* hits_voxel_idx, void* stream);
+
+/* vren.ray_sphere_intersect (binding.cpp:19-31, intersection.cu:103-197). */
+int ngp_ray_sphere_intersect(const float* rays_o, const float* rays_d, const float* centers, const float* radii,
+                             int n_rays, int n_spheres, int max_hits, int* hit_cnt, float* hits_t,
+                             int64_t* hits_sphere_idx, void* stream);
+
+/* vren.packbits (binding.cpp:34-43, raymarching.cu:122-161). dtype 0=f32 1=f16 2=f64; n_bytes = size of
+ * density_bitfield; optional thr_dev (device float*): effective threshold = min(thr, *thr_dev), which
+ * keeps `min(mean_density, thr)` of networks.py:266-269 on the device. */
+int ngp_packbits(const void* density_grid, int dtype, int64_t n_bytes, float thr, const float* thr_dev,
+                 uint8_t* density_bitfield, void* stream);
+
+/* vren.morton3D / vren.morton3D_invert (binding.cpp:46-57, raymarching.cu:62-119); coords int32 (n,3). */
+int ngp_morton3D(const int* coords, int n, int* indices, void* stream);
+int ngp_morton3D_invert(const int* indices, int n, int* coords, void* stream);
+
+/* vren.raymarching_train (binding.cpp:60-81, raymarching.cu:166-332). hits_t is (n_rays,2). Outputs:
+ * rays_a int64 (n_rays,3) = [ray_idx,start_idx,N_samples] ordered by ray index; xyzs,dirs (>=total,3);
+ * deltas,ts (>=total); counter int32[2] = [total_samples, n_rays]. Rows past `total` are not written. */
+size_t ngp_raymarching_train_workspace(int n_rays);
+int ngp_raymarching_train(const float* rays_o, const float* rays_d, const float* hits_t,
+                          const uint8_t* density_bitfield, int cascades, float scale, float exp_step_factor,
+                          const float* noise, int grid_size, int max_samples, int n_rays,
+                          int64_t* rays_a, float* xyzs, float* dirs, float* deltas, float* ts, int* counter,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* vren.raymarching_test (binding.cpp:84-106, raymarching.cu:335-454). hits_t (n_rays_total,2) is
+ * MUTATED ([r][0] advanced); outputs are (n_alive,N_samples[,3]) with zero padding. */
+int ngp_raymarching_test(const float* rays_o, const float* rays_d, float* hits_t, const int64_t* alive_indices,
+                         const uint8_t* density_bitfield, int cascades, float scale, float exp_step_factor,
+                         int grid_size, int max_samples, int N_samples, int n_alive,
+                         float* xyzs, float* dirs, float* deltas, float* ts, int* N_eff_samples, void* stream);
+
+/* vren.composite_train_fw (binding.cpp:109-126, volumerendering.cu:6-84). */
+int ngp_composite_train_fw(const float* sigmas, const float* rgbs, const float* deltas, const float* ts,
+                           const int64_t* rays_a, float T_threshold, int n_rays, int64_t n_samples,
+                           int64_t* total_samples, float* opacity, float* depth, float* rgb, float* ws, void* stream);
+
+/* vren.composite_train_bw (binding.cpp:129-163, volumerendering.cu:87-202). */
+int ngp_composite_train_bw(const float* dL_dopacity, const float* dL_ddepth, const float* dL_drgb, const float* dL_dws,
+                           const float* sigmas, const float* rgbs, const float* ws, const float* deltas, const float* ts,
+                           const int64_t* rays_a, const float* opacity, const float* depth, const float* rgb,
+                           float T_threshold, int n_rays, int64_t n_samples, float* dL_dsigmas, float* dL_drgbs,
+                           void* stream);
+
+/* vren.composite_test_fw (binding.cpp:166-194, volumerendering.cu:205-285); alive_indices, opacity,
+ * depth, rgb are updated in place. */
+int ngp_composite_test_fw(const float* sigmas, const float* rgbs, const float* deltas, const float* ts,
+                          const float* hits_t, int64_t* alive_indices, float T_threshold, const int* N_eff_samples,
+                          int n_alive, int N_samples, float* opacity, float* depth, float* rgb, void* stream);
+
+/* vren.distortion_loss_fw / _bw (binding.cpp:197-231, losses.cu:10-174). */
+int ngp_distortion_loss_fw(const float* ws, const float* deltas, const float* ts, const int64_t* rays_a, int n_rays,
+                           int64_t n_samples, float* loss, float* ws_inclusive_scan, float* wts_inclusive_scan,
+                           void* stream);
+int ngp_distortion_loss_bw(const float* dL_dloss, const float* ws_inclusive_scan, const float* wts_inclusive_scan,
+                           const float* ws, const float* deltas, const float* ts, const int64_t* rays_a, int n_rays,
+                           int64_t n_samples, float* dL_dws, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * The network the reference builds from tinycudann modules (models/networks.py:36-77):
+ *   xyz_encoder = HashGrid(L levels, F=2, T=2^log2_T, N_min, b) -> MLP 32->64(ReLU)->16
+ *   dir_encoder = SH degree 4 ;  rgb_net = MLP 32->64->64->3(pad 16), Sigmoid
+ * Parameter layout (tinycudann's): xyz_encoder.params = [W1 64x32 | W2 16x64 | table entries*2],
+ * rgb_net.params = [W1 64x32 | W2 64x64 | W3 16x64], every matrix row-major (out,in).
+ * -------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t n_levels;
+    uint32_t hashed_mask;                 /* bit l set: level l is hashed (res^3 > entries) */
+    uint32_t offset[NGP_MAX_LEVELS + 1];  /* in entries (one entry = F=2 features) */
+    uint32_t res[NGP_MAX_LEVELS];
+    float scale[NGP_MAX_LEVELS];
+} NgpGridMeta;
+
+/* Host-side: level table of the hash grid (no GPU needed). Returns total entries, 0 on bad input. */
+uint32_t ngp_grid_meta(int n_levels, int log2_hashmap_size, int base_resolution, float per_level_scale,
+                       NgpGridMeta* out);
+
+#define NGP_DENSITY_MLP_PARAMS 3072 /* 64*32 + 16*64 */
+#define NGP_RGB_MLP_PARAMS 7168     /* 64*32 + 64*64 + 16*64 */
+
+/* fp32 -> fp16 working copy of a parameter vector (tinycudann casts its fp32 params every forward). */
+int ngp_cast_params(const float* src, uint16_t* dst_half, int64_t n, void* stream);
+
+typedef struct {
+    const uint16_t* enc_params_h; /* fp16 xyz_encoder params: [3072 MLP | table] */
+    const uint16_t* rgb_params_h; /* fp16 rgb_net params (7168) */
+    NgpGridMeta meta;
+    float xyz_min[3];
+    float xyz_max[3];
+    int32_t rgb_act; /* 1 = Sigmoid (reference default), 0 = None */
+} NgpNet;
+
+/* Sample positions are given EITHER as xyzs+dirs (n,3) arrays (ray_idx == NULL) -- the signature of
+ * NGP.forward(x, d), networks.py:132 -- OR as (rays_o, rays_d, ray_idx, ts): x = fma(d, t, o). */
+typedef struct {
+    const float* xyzs;
+    const float* dirs;
+    const float* rays_o;
+    const float* rays_d;
+    const int32_t* ray_idx;
+    const float* ts;
+    int64_t n;
+} NgpSamples;
+
+/* Fused forward of NGP.forward (networks.py:132-153): hash gather + trilinear + density MLP +
+ * exp + SH + rgb MLP + sigmoid, one kernel. sigmas fp32 (n), rgbs fp32 (n,3) (values are
+ * fp16-representable, as tinycudann returns fp16). feat_save (optional, 64 B/sample, opaque fragment
+ * order) keeps the encoded features for ngp_net_backward. want_rgb = 0 evaluates NGP.density only. */
+int ngp_net_forward(const NgpNet* net, const NgpSamples* smp, int want_rgb, float* sigmas, float* rgbs,
+                    uint16_t* h_out /* optional fp16 (n,16) */, void* feat_save /* 16-B aligned */, void* stream);
+
+size_t ngp_net_backward_workspace(void);
+/* Fused backward: recomputes the MLP activations from feat_save (or by re-gathering when NULL),
+ * back-propagates dL/dsigmas (n) and dL/drgbs (n,3), accumulates
+ *   grad_enc (fp32, same layout as xyz_encoder.params) and grad_rgb (fp32, 7168)   with atomics (+=).
+ * loss_scale (device float*, optional) is the power-of-two the fp16 gradient operands are scaled by
+ * internally (results are un-scaled); NULL = 1. */
+int ngp_net_backward(const NgpNet* net, const NgpSamples* smp, const float* dL_dsigmas, const float* dL_drgbs,
+                     const void* feat_save, const float* loss_scale, float* grad_enc, float* grad_rgb,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* loss_scale helper: *scale_out = 2^floor(log2(256 / max(|dL_dsigmas*sigma'|, |dL_drgbs|))) (1 if all zero). */
+int ngp_grad_scale(const float* dL_dsigmas, const float* sigmas, const float* dL_drgbs, int64_t n,
+                   float* scratch /* 1 float */, float* scale_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGP_B200_H */

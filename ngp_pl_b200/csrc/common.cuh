@@ -1,0 +1,78 @@
+// Shared helpers for the sm_100a kernels of the ngp_pl hot path.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#define NGP_WARP 32
+
+// Every C-ABI entry point returns 0 on success, a cudaError_t (>0) on a CUDA failure,
+// or NGP_EINVAL (<0) for an argument the op cannot honour. Nothing allocates.
+#define NGP_EINVAL (-22)
+
+#define NGP_CHECK_LAUNCH()                                   \
+    do {                                                     \
+        cudaError_t _e = cudaGetLastError();                 \
+        if (_e != cudaSuccess) return (int)_e;               \
+    } while (0)
+
+#define NGP_CUDA(call)                                       \
+    do {                                                     \
+        cudaError_t _e = (call);                             \
+        if (_e != cudaSuccess) return (int)_e;               \
+    } while (0)
+
+static inline int ngp_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Number of SMs of the current device (148 on B200); cached per process.
+static inline int ngp_sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// inclusive scans across the 32 lanes of a warp
+__device__ __forceinline__ float warp_scan_add(float v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        float u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+    }
+    return v;
+}
+__device__ __forceinline__ float warp_scan_mul(float v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        float u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v *= u;
+    }
+    return v;
+}
+
+// 8-byte vector reduction (two fp32 adds in one L2 atomic transaction; sm_90+)
+__device__ __forceinline__ void red_add_f32x2(float* addr, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_half2(uint32_t u) {
+    __half2 h = *reinterpret_cast<__half2*>(&u);
+    return __half22float2(h);
+}

@@ -1,0 +1,634 @@
+// Fused NGP network kernels for sm_100a: hash-grid gather + trilinear interpolation + density MLP +
+// exp + SH-4 + rgb MLP + sigmoid in ONE forward kernel, and ONE backward kernel that recomputes the
+// activations, runs dgrad/wgrad on the tensor cores and scatters hash-table gradients with 8-byte
+// vector reductions. Replaces the three tinycudann modules of reference models/networks.py:36-77 and
+// the glue of NGP.density / NGP.forward (networks.py:94-107, :132-153).
+#include "common.cuh"
+#include "hashgrid.cuh"
+#include "mlp.cuh"
+#include "../../include/ngp_b200.h"
+#include <math.h>
+
+extern "C" int ngp_abi_version(void) { return NGP_ABI_VERSION; }
+
+// -------------------------------------------------------------------------------------------------
+// host: level table (tiny-cuda-nn GridEncoding constructor semantics)
+// -------------------------------------------------------------------------------------------------
+extern "C" uint32_t ngp_grid_meta(int n_levels, int log2_hashmap_size, int base_resolution, float per_level_scale,
+                                  NgpGridMeta* out) {
+    if (!out || n_levels < 1 || n_levels > NGP_MAX_LEVELS || log2_hashmap_size < 3 || log2_hashmap_size > 28 ||
+        base_resolution < 1 || !(per_level_scale >= 1.0f))
+        return 0;
+    const float log2_b = log2f(per_level_scale);
+    uint64_t offset = 0;
+    out->n_levels = n_levels;
+    out->hashed_mask = 0;
+    for (int l = 0; l < NGP_MAX_LEVELS; ++l) {
+        out->offset[l] = 0; out->res[l] = 0; out->scale[l] = 0.f;
+    }
+    for (int l = 0; l < n_levels; ++l) {
+        const float scale = exp2f((float)l * log2_b) * (float)base_resolution - 1.0f;
+        const uint32_t res = (uint32_t)ceilf(scale) + 1u;
+        const uint64_t dense = (uint64_t)res * res * res;
+        uint64_t entries = (dense + 7u) / 8u * 8u;
+        const uint64_t cap = 1ull << log2_hashmap_size;
+        if (entries > cap) entries = cap;
+        if (dense > entries) out->hashed_mask |= (1u << l);
+        out->offset[l] = (uint32_t)offset;
+        out->res[l] = res;
+        out->scale[l] = scale;
+        offset += entries;
+        if (offset > 0xffffffffull) return 0;
+    }
+    for (int l = n_levels; l <= NGP_MAX_LEVELS; ++l) out->offset[l] = (uint32_t)offset;
+    return (uint32_t)offset;
+}
+
+// -------------------------------------------------------------------------------------------------
+// fp32 master params -> fp16 working copy
+// -------------------------------------------------------------------------------------------------
+__global__ void k_cast_params(const float* __restrict__ src, __half* __restrict__ dst, int64_t n) {
+    const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n && ((((uintptr_t)src) & 15) == 0) && ((((uintptr_t)dst) & 7) == 0)) {
+        const float4 v = *reinterpret_cast<const float4*>(src + i);
+        uint2 o;
+        o.x = pack_half2(v.x, v.y);
+        o.y = pack_half2(v.z, v.w);
+        *reinterpret_cast<uint2*>(dst + i) = o;
+    } else {
+        for (int64_t k = i; k < n && k < i + 4; ++k) dst[k] = __float2half_rn(src[k]);
+    }
+}
+extern "C" int ngp_cast_params(const float* src, uint16_t* dst_half, int64_t n, void* stream) {
+    if (n < 0) return NGP_EINVAL;
+    if (n == 0) return 0;
+    k_cast_params<<<ngp_div_up((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(src, (__half*)dst_half, n);
+    NGP_CHECK_LAUNCH();
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// sample access
+// -------------------------------------------------------------------------------------------------
+struct SampleIn {
+    float x, y, z;     // world position
+    float dx, dy, dz;  // (unnormalised) view direction
+};
+__device__ __forceinline__ SampleIn load_sample(const NgpSamples& s, int64_t i, bool valid) {
+    SampleIn o;
+    if (!valid) {
+        o.x = o.y = o.z = 0.f;
+        o.dx = 0.f; o.dy = 0.f; o.dz = 1.f;
+        return o;
+    }
+    if (s.ray_idx) {
+        const int r = __ldg(s.ray_idx + i);
+        const float t = __ldg(s.ts + i);
+        o.dx = __ldg(s.rays_d + 3 * r); o.dy = __ldg(s.rays_d + 3 * r + 1); o.dz = __ldg(s.rays_d + 3 * r + 2);
+        // same rounding as the marcher's sample position (march.cuh: x = fma(d, t, o))
+        o.x = __fmaf_rn(o.dx, t, __ldg(s.rays_o + 3 * r));
+        o.y = __fmaf_rn(o.dy, t, __ldg(s.rays_o + 3 * r + 1));
+        o.z = __fmaf_rn(o.dz, t, __ldg(s.rays_o + 3 * r + 2));
+    } else {
+        o.x = __ldg(s.xyzs + 3 * i); o.y = __ldg(s.xyzs + 3 * i + 1); o.z = __ldg(s.xyzs + 3 * i + 2);
+        if (s.dirs) {
+            o.dx = __ldg(s.dirs + 3 * i); o.dy = __ldg(s.dirs + 3 * i + 1); o.dz = __ldg(s.dirs + 3 * i + 2);
+        } else {
+            o.dx = 0.f; o.dy = 0.f; o.dz = 1.f;
+        }
+    }
+    return o;
+}
+
+__device__ __forceinline__ float sel4(int q, float a, float b, float c, float d) {
+    return q == 0 ? a : (q == 1 ? b : (q == 2 ? c : d));
+}
+
+// x01 = (x - xyz_min) / (xyz_max - xyz_min)   (reference networks.py:103)
+__device__ __forceinline__ void to_unit(const NgpNet& net, const SampleIn& s, float& u, float& v, float& w) {
+    u = __fdiv_rn(s.x - net.xyz_min[0], net.xyz_max[0] - net.xyz_min[0]);
+    v = __fdiv_rn(s.y - net.xyz_min[1], net.xyz_max[1] - net.xyz_min[1]);
+    w = __fdiv_rn(s.z - net.xyz_min[2], net.xyz_max[2] - net.xyz_min[2]);
+}
+
+// Encode the rows this lane owns into the A fragments of the first density layer.
+// Lane (g,q) owns rows {g, g+8} of each 16-row tile and levels {q, q+4, q+8, q+12}.
+template <int MT>
+__device__ __forceinline__ void encode_rows(const NgpNet& net, const uint32_t* __restrict__ table,
+                                            const float (&u)[MT][2][3], const bool (&valid)[MT][2],
+                                            uint32_t (&featA)[MT][2][4], int q) {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int level = 4 * j + q;
+                float2 f = make_float2(0.f, 0.f);
+                if (valid[mt][h] && level < net.meta.n_levels)
+                    f = grid_lookup(table, net.meta, level, u[mt][h][0], u[mt][h][1], u[mt][h][2]);
+                featA[mt][j >> 1][2 * (j & 1) + h] = pack_half2(f.x, f.y);
+            }
+}
+
+// SH-4 of the normalised direction, as the A fragment k-tile 0 of the rgb net input.
+__device__ __forceinline__ void sh_rows(const SampleIn& s, int q, uint32_t& lo, uint32_t& hi) {
+    const float inv = 1.0f / sqrtf(s.dx * s.dx + s.dy * s.dy + s.dz * s.dz);
+    float sh[16];
+    sh4(s.dx * inv, s.dy * inv, s.dz * inv, sh);
+    lo = pack_half2(sel4(q, sh[0], sh[2], sh[4], sh[6]), sel4(q, sh[1], sh[3], sh[5], sh[7]));
+    hi = pack_half2(sel4(q, sh[8], sh[10], sh[12], sh[14]), sel4(q, sh[9], sh[11], sh[13], sh[15]));
+}
+
+__device__ __forceinline__ float half_round(float v) { return __half2float(__float2half_rn(v)); }
+__device__ __forceinline__ float lo_half(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u & 0xffffu))); }
+__device__ __forceinline__ float hi_half(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u >> 16))); }
+
+// -------------------------------------------------------------------------------------------------
+// forward
+// -------------------------------------------------------------------------------------------------
+#define FWD_THREADS 256
+#define FWD_MT 2
+
+__global__ void __launch_bounds__(FWD_THREADS, 1)
+k_ngp_fwd(const NgpNet net, const NgpSamples smp, const int want_rgb, float* __restrict__ sigmas, float* __restrict__ rgbs,
+          __half* __restrict__ h_out, uint4* __restrict__ feat_save) {
+    __shared__ MlpWeightsFwd sw;
+    const __half* wd = reinterpret_cast<const __half*>(net.enc_params_h);
+    const __half* wr = want_rgb ? reinterpret_cast<const __half*>(net.rgb_params_h) : nullptr;
+    load_weights_fwd(sw, wd, wr, threadIdx.x, FWD_THREADS);
+    __syncthreads();
+    const uint32_t* table = reinterpret_cast<const uint32_t*>(wd + NGP_DENSITY_MLP_PARAMS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    const int64_t n = smp.n;
+    const int64_t n_tiles = (n + 16 * FWD_MT - 1) / (16 * FWD_MT);
+    const int warps_per_cta = FWD_THREADS / 32;
+
+    for (int64_t tile = (int64_t)blockIdx.x * warps_per_cta + warp; tile < n_tiles; tile += (int64_t)gridDim.x * warps_per_cta) {
+        const int64_t base = tile * 16 * FWD_MT;
+        SampleIn sm[FWD_MT][2];
+        bool valid[FWD_MT][2];
+        float u[FWD_MT][2][3];
+#pragma unroll
+        for (int mt = 0; mt < FWD_MT; ++mt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int64_t row = base + 16 * mt + g + 8 * h;
+                valid[mt][h] = row < n;
+                sm[mt][h] = load_sample(smp, row, valid[mt][h]);
+                to_unit(net, sm[mt][h], u[mt][h][0], u[mt][h][1], u[mt][h][2]);
+            }
+
+        uint32_t featA[FWD_MT][2][4];
+        encode_rows<FWD_MT>(net, table, u, valid, featA, q);
+
+        if (feat_save) {
+#pragma unroll
+            for (int mt = 0; mt < FWD_MT; ++mt)
+#pragma unroll
+                for (int kt = 0; kt < 2; ++kt)
+                    feat_save[((tile * FWD_MT + mt) * 2 + kt) * 32 + lane] =
+                        make_uint4(featA[mt][kt][0], featA[mt][kt][1], featA[mt][kt][2], featA[mt][kt][3]);
+        }
+
+        // density MLP: 32 -> 64 (ReLU) -> 16
+        uint32_t hidA[FWD_MT][4][4];
+        {
+            float hidC[FWD_MT][8][4];
+            mlp_layer<FWD_MT, 32, 64, LD32>(featA, sw.w1d, hidC, g, q);
+            relu_to_frag<FWD_MT, 64>(hidC, hidA);
+        }
+        uint32_t hA[FWD_MT][1][4];
+        {
+            float hC[FWD_MT][2][4];
+            mlp_layer<FWD_MT, 64, 16, LD64>(hidA, sw.w2d, hC, g, q);
+            to_frag<FWD_MT, 16>(hC, hA);  // tinycudann returns fp16
+        }
+#pragma unroll
+        for (int mt = 0; mt < FWD_MT; ++mt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int64_t row = base + 16 * mt + g + 8 * h;
+                if (valid[mt][h]) {
+                    // sigma = exp(h[:,0]) in fp32 (reference networks.py:105, custom_functions.py:162-167)
+                    if (q == 0) sigmas[row] = expf(lo_half(hA[mt][0][h]));
+                    if (h_out) {
+                        uint32_t* ho = reinterpret_cast<uint32_t*>(h_out + row * 16);
+                        ho[q] = hA[mt][0][h];
+                        ho[4 + q] = hA[mt][0][2 + h];
+                    }
+                }
+            }
+        if (!want_rgb) continue;
+
+        // rgb MLP input: [SH16(dir) | h16]
+        uint32_t inA[FWD_MT][2][4];
+#pragma unroll
+        for (int mt = 0; mt < FWD_MT; ++mt) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) sh_rows(sm[mt][h], q, inA[mt][0][h], inA[mt][0][2 + h]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) inA[mt][1][e] = hA[mt][0][e];
+        }
+        uint32_t r1A[FWD_MT][4][4];
+        {
+            float c[FWD_MT][8][4];
+            mlp_layer<FWD_MT, 32, 64, LD32>(inA, sw.w1r, c, g, q);
+            relu_to_frag<FWD_MT, 64>(c, r1A);
+        }
+        uint32_t r2A[FWD_MT][4][4];
+        {
+            float c[FWD_MT][8][4];
+            mlp_layer<FWD_MT, 64, 64, LD64>(r1A, sw.w2r, c, g, q);
+            relu_to_frag<FWD_MT, 64>(c, r2A);
+        }
+        float oC[FWD_MT][1][4];
+        mlp_layer<FWD_MT, 64, 8, LD64>(r2A, sw.w3r, oC, g, q);  // only output columns 0..7 are needed (rgb = 0..2)
+#pragma unroll
+        for (int mt = 0; mt < FWD_MT; ++mt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int64_t row = base + 16 * mt + g + 8 * h;
+                if (!valid[mt][h] || q > 1) continue;
+                float a = oC[mt][0][2 * h], b = oC[mt][0][2 * h + 1];
+                if (net.rgb_act == 1) {
+                    a = 1.0f / (1.0f + __expf(-a));
+                    b = 1.0f / (1.0f + __expf(-b));
+                }
+                a = half_round(a);
+                b = half_round(b);
+                if (q == 0) {
+                    rgbs[3 * row] = a;
+                    rgbs[3 * row + 1] = b;
+                } else {
+                    rgbs[3 * row + 2] = a;
+                }
+            }
+    }
+}
+
+extern "C" int ngp_net_forward(const NgpNet* net, const NgpSamples* smp, int want_rgb, float* sigmas, float* rgbs,
+                               uint16_t* h_out, void* feat_save, void* stream) {
+    if (!net || !smp || smp->n < 0 || !sigmas || (want_rgb && !rgbs)) return NGP_EINVAL;
+    if (net->meta.n_levels < 1 || net->meta.n_levels > NGP_MAX_LEVELS) return NGP_EINVAL;
+    if (smp->n == 0) return 0;
+    const int64_t n_tiles = (smp->n + 16 * FWD_MT - 1) / (16 * FWD_MT);
+    const int64_t want = (n_tiles + FWD_THREADS / 32 - 1) / (FWD_THREADS / 32);
+    const int grid = (int)(want < (int64_t)ngp_sm_count() ? want : ngp_sm_count());
+    k_ngp_fwd<<<grid, FWD_THREADS, 0, (cudaStream_t)stream>>>(*net, *smp, want_rgb, sigmas, rgbs, (__half*)h_out,
+                                                              (uint4*)feat_save);
+    NGP_CHECK_LAUNCH();
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// backward
+// -------------------------------------------------------------------------------------------------
+#define BWD_WARPS 8
+#define BWD_THREADS (BWD_WARPS * 32)
+#define BWD_ROWS (BWD_WARPS * 16)
+
+// per-CTA staging of the operands of the five weight-gradient GEMMs, [sample][channel] fp16
+struct BwdStage {
+    __half feat[BWD_ROWS * LD32];  // in  of W1d
+    __half hid[BWD_ROWS * LD64];   // in  of W2d
+    __half rin[BWD_ROWS * LD32];   // in  of W1r
+    __half r1[BWD_ROWS * LD64];    // in  of W2r
+    __half r2[BWD_ROWS * LD64];    // in  of W3r
+    __half dhid[BWD_ROWS * LD64];  // out-grad of W1d
+    __half dh[BWD_ROWS * LD16];    // out-grad of W2d
+    __half dr1[BWD_ROWS * LD64];   // out-grad of W1r
+    __half dr2[BWD_ROWS * LD64];   // out-grad of W2r
+    __half dout[BWD_ROWS * LD16];  // out-grad of W3r
+};
+struct BwdSmem {
+    MlpWeightsFwd wf;
+    MlpWeightsBwd wb;
+    BwdStage st;
+};
+
+template <int KT>
+__device__ __forceinline__ void stage_frag(__half* __restrict__ dst, int ld, int row0, const uint32_t (&A)[KT][4], int g, int q) {
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+        uint32_t* r0 = reinterpret_cast<uint32_t*>(dst + (row0 + g) * ld + 16 * kt + 2 * q);
+        uint32_t* r1 = reinterpret_cast<uint32_t*>(dst + (row0 + g + 8) * ld + 16 * kt + 2 * q);
+        r0[0] = A[kt][0];
+        r1[0] = A[kt][1];
+        r0[4] = A[kt][2];
+        r1[4] = A[kt][3];
+    }
+}
+
+// one 16x8 tile of dW = dOut^T * In accumulated over the BWD_ROWS staged samples
+__device__ __forceinline__ void wgrad_tile(float (&acc)[4], const __half* __restrict__ dOut, int ld_o, int mt,
+                                           const __half* __restrict__ In, int ld_i, int nt, int lane) {
+    const int ra = (lane & 7) + 8 * ((lane >> 4) & 1);  // sample row inside the 16-row k-step (A operand tiles)
+    const int ca = 16 * mt + 8 * ((lane >> 3) & 1);     // out-channel column of the tile this lane addresses
+    const int rb = (lane & 7) + 8 * ((lane >> 3) & 1);  // sample row for the two B tiles
+    const int cb = 8 * nt;
+#pragma unroll
+    for (int ks = 0; ks < BWD_ROWS / 16; ++ks) {
+        uint32_t a[4], b0, b1;
+        ldmatrix_x4_trans(a, dOut + (16 * ks + ra) * ld_o + ca);
+        ldmatrix_x2_trans(b0, b1, In + (16 * ks + rb) * ld_i + cb);
+        mma_16816(acc, a, b0, b1);
+    }
+}
+
+__device__ __forceinline__ void wgrad_flush(const float (&acc)[4], float* __restrict__ dW, int in_dim, int mt, int nt,
+                                            float inv_scale, int g, int q) {
+    float* p0 = dW + (16 * mt + g) * in_dim + 8 * nt + 2 * q;
+    float* p1 = dW + (16 * mt + g + 8) * in_dim + 8 * nt + 2 * q;
+    red_add_f32x2(p0, acc[0] * inv_scale, acc[1] * inv_scale);
+    red_add_f32x2(p1, acc[2] * inv_scale, acc[3] * inv_scale);
+}
+
+// wgrad tile table: 80 (matrix, out-tile, in-tile) triples, 10 per warp
+struct WgradTile {
+    int mat, mt, nt;
+};
+__device__ __forceinline__ WgradTile wgrad_tile_of(int t) {
+    WgradTile w;
+    if (t < 16) { w.mat = 0; w.mt = t >> 2; w.nt = t & 3; }                 // dW1d 64x32
+    else if (t < 24) { w.mat = 1; w.mt = 0; w.nt = t - 16; }                // dW2d 16x64
+    else if (t < 40) { w.mat = 2; w.mt = (t - 24) >> 2; w.nt = (t - 24) & 3; }  // dW1r 64x32
+    else if (t < 72) { w.mat = 3; w.mt = (t - 40) >> 3; w.nt = (t - 40) & 7; }  // dW2r 64x64
+    else { w.mat = 4; w.mt = 0; w.nt = t - 72; }                            // dW3r 16x64
+    return w;
+}
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+k_ngp_bwd(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_dsigmas, const float* __restrict__ dL_drgbs,
+          const uint4* __restrict__ feat_save, const float* __restrict__ loss_scale, float* __restrict__ grad_enc,
+          float* __restrict__ grad_rgb) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BwdSmem& S = *reinterpret_cast<BwdSmem*>(smem_raw);
+    const __half* wd = reinterpret_cast<const __half*>(net.enc_params_h);
+    const __half* wr = reinterpret_cast<const __half*>(net.rgb_params_h);
+    load_weights_fwd(S.wf, wd, wr, threadIdx.x, BWD_THREADS);
+    load_weights_bwd(S.wb, wd, wr, threadIdx.x, BWD_THREADS);
+    __syncthreads();
+    const uint32_t* table = reinterpret_cast<const uint32_t*>(wd + NGP_DENSITY_MLP_PARAMS);
+    float* grad_table = grad_enc + NGP_DENSITY_MLP_PARAMS;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    const int64_t n = smp.n;
+    const int64_t n_mtiles = (n + 15) / 16;
+    const int64_t n_blks = (n_mtiles + BWD_WARPS - 1) / BWD_WARPS;
+    const float scale = loss_scale ? *loss_scale : 1.0f;
+    const float inv_scale = 1.0f / scale;
+
+    float acc[10][4];
+#pragma unroll
+    for (int j = 0; j < 10; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+
+    for (int64_t blk = blockIdx.x; blk < n_blks; blk += gridDim.x) {
+        const int64_t mtile = blk * BWD_WARPS + warp;
+        const int64_t base = mtile * 16;
+        SampleIn sm[1][2];
+        bool valid[1][2];
+        float u[1][2][3];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t row = base + g + 8 * h;
+            valid[0][h] = row < n;
+            sm[0][h] = load_sample(smp, row, valid[0][h]);
+            to_unit(net, sm[0][h], u[0][h][0], u[0][h][1], u[0][h][2]);
+        }
+
+        // ---- recompute the forward activations ----
+        uint32_t featA[1][2][4];
+        if (feat_save && base < n) {
+#pragma unroll
+            for (int kt = 0; kt < 2; ++kt) {
+                const uint4 v = __ldg(feat_save + (mtile * 2 + kt) * 32 + lane);
+                featA[0][kt][0] = v.x; featA[0][kt][1] = v.y; featA[0][kt][2] = v.z; featA[0][kt][3] = v.w;
+            }
+        } else {
+            encode_rows<1>(net, table, u, valid, featA, q);
+        }
+        uint32_t hidA[1][4][4];
+        {
+            float c[1][8][4];
+            mlp_layer<1, 32, 64, LD32>(featA, S.wf.w1d, c, g, q);
+            relu_to_frag<1, 64>(c, hidA);
+        }
+        uint32_t hA[1][1][4];
+        {
+            float c[1][2][4];
+            mlp_layer<1, 64, 16, LD64>(hidA, S.wf.w2d, c, g, q);
+            to_frag<1, 16>(c, hA);
+        }
+        uint32_t inA[1][2][4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) sh_rows(sm[0][h], q, inA[0][0][h], inA[0][0][2 + h]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) inA[0][1][e] = hA[0][0][e];
+        uint32_t r1A[1][4][4];
+        {
+            float c[1][8][4];
+            mlp_layer<1, 32, 64, LD32>(inA, S.wf.w1r, c, g, q);
+            relu_to_frag<1, 64>(c, r1A);
+        }
+        uint32_t r2A[1][4][4];
+        {
+            float c[1][8][4];
+            mlp_layer<1, 64, 64, LD64>(r1A, S.wf.w2r, c, g, q);
+            relu_to_frag<1, 64>(c, r2A);
+        }
+        float oC[1][1][4];
+        mlp_layer<1, 64, 8, LD64>(r2A, S.wf.w3r, oC, g, q);
+
+        // ---- output gradients (scaled by the power-of-two loss scale before the fp16 cast) ----
+        uint32_t doutA[1][1][4];
+        doutA[0][0][2] = 0u;
+        doutA[0][0][3] = 0u;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t row = base + g + 8 * h;
+            float d0 = 0.f, d1 = 0.f;
+            if (valid[0][h] && q < 2) {
+                float o0 = oC[0][0][2 * h], o1 = oC[0][0][2 * h + 1];
+                float s0 = 1.f, s1 = 1.f;
+                if (net.rgb_act == 1) {
+                    o0 = half_round(1.0f / (1.0f + __expf(-o0)));
+                    o1 = half_round(1.0f / (1.0f + __expf(-o1)));
+                    s0 = o0 * (1.0f - o0);
+                    s1 = o1 * (1.0f - o1);
+                }
+                if (q == 0) {
+                    d0 = __ldg(dL_drgbs + 3 * row) * s0 * scale;
+                    d1 = __ldg(dL_drgbs + 3 * row + 1) * s1 * scale;
+                } else {
+                    d0 = __ldg(dL_drgbs + 3 * row + 2) * s0 * scale;
+                }
+            }
+            doutA[0][0][h] = pack_half2(d0, d1);
+        }
+
+        // ---- dgrad chain of the rgb net ----
+        uint32_t dr2A[1][4][4];
+        {
+            float c[1][8][4];
+            mlp_layer<1, 16, 64, LD16>(doutA, S.wb.w3rT, c, g, q);
+            relu_bwd_to_frag<1, 64>(c, r2A, dr2A);
+        }
+        uint32_t dr1A[1][4][4];
+        {
+            float c[1][8][4];
+            mlp_layer<1, 64, 64, LD64>(dr2A, S.wb.w2rT, c, g, q);
+            relu_bwd_to_frag<1, 64>(c, r1A, dr1A);
+        }
+        // gradient w.r.t. the h half of the rgb-net input (columns 16..31); SH columns need no gradient
+        uint32_t dhA[1][1][4];
+        {
+            float c[1][2][4];
+            mlp_layer<1, 64, 16, LD64>(dr1A, S.wb.w1rT + 16 * LD64, c, g, q);
+            // + density branch: d sigma / d h0 = exp(clamp(h0, -15, 15))  (reference custom_functions.py:169-173)
+            if (q == 0) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int64_t row = base + g + 8 * h;
+                    if (valid[0][h]) {
+                        const float h0 = lo_half(hA[0][0][h]);
+                        c[0][0][2 * h] += __ldg(dL_dsigmas + row) * expf(fminf(fmaxf(h0, -15.f), 15.f)) * scale;
+                    }
+                }
+            }
+            to_frag<1, 16>(c, dhA);
+        }
+        uint32_t dhidA[1][4][4];
+        {
+            float c[1][8][4];
+            mlp_layer<1, 16, 64, LD16>(dhA, S.wb.w2dT, c, g, q);
+            relu_bwd_to_frag<1, 64>(c, hidA, dhidA);
+        }
+        // ---- gradient of the encoded features, scattered straight into the fp32 table gradient ----
+        {
+            float c[1][4][4];
+            mlp_layer<1, 64, 32, LD64>(dhidA, S.wb.w1dT, c, g, q);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (!valid[0][h]) continue;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int level = 4 * j + q;
+                    if (level < net.meta.n_levels)
+                        grid_scatter(grad_table, net.meta, level, u[0][h][0], u[0][h][1], u[0][h][2],
+                                     c[0][j][2 * h] * inv_scale, c[0][j][2 * h + 1] * inv_scale);
+                }
+            }
+        }
+
+        // ---- stage the wgrad operands and run the five dW GEMMs over this CTA's 128 samples ----
+        const int row0 = 16 * warp;
+        stage_frag<2>(S.st.feat, LD32, row0, featA[0], g, q);
+        stage_frag<4>(S.st.hid, LD64, row0, hidA[0], g, q);
+        stage_frag<2>(S.st.rin, LD32, row0, inA[0], g, q);
+        stage_frag<4>(S.st.r1, LD64, row0, r1A[0], g, q);
+        stage_frag<4>(S.st.r2, LD64, row0, r2A[0], g, q);
+        stage_frag<4>(S.st.dhid, LD64, row0, dhidA[0], g, q);
+        stage_frag<1>(S.st.dh, LD16, row0, dhA[0], g, q);
+        stage_frag<4>(S.st.dr1, LD64, row0, dr1A[0], g, q);
+        stage_frag<4>(S.st.dr2, LD64, row0, dr2A[0], g, q);
+        stage_frag<1>(S.st.dout, LD16, row0, doutA[0], g, q);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+            const WgradTile w = wgrad_tile_of(warp * 10 + j);
+            const __half* dO; const __half* In; int ldo, ldi;
+            switch (w.mat) {
+                case 0: dO = S.st.dhid; ldo = LD64; In = S.st.feat; ldi = LD32; break;
+                case 1: dO = S.st.dh; ldo = LD16; In = S.st.hid; ldi = LD64; break;
+                case 2: dO = S.st.dr1; ldo = LD64; In = S.st.rin; ldi = LD32; break;
+                case 3: dO = S.st.dr2; ldo = LD64; In = S.st.r1; ldi = LD64; break;
+                default: dO = S.st.dout; ldo = LD16; In = S.st.r2; ldi = LD64; break;
+            }
+            wgrad_tile(acc[j], dO, ldo, w.mt, In, ldi, w.nt, lane);
+        }
+        __syncthreads();
+    }
+
+    // ---- flush the per-warp weight-gradient tiles ----
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+        const WgradTile w = wgrad_tile_of(warp * 10 + j);
+        switch (w.mat) {
+            case 0: wgrad_flush(acc[j], grad_enc, 32, w.mt, w.nt, inv_scale, g, q); break;
+            case 1: wgrad_flush(acc[j], grad_enc + 2048, 64, w.mt, w.nt, inv_scale, g, q); break;
+            case 2: wgrad_flush(acc[j], grad_rgb, 32, w.mt, w.nt, inv_scale, g, q); break;
+            case 3: wgrad_flush(acc[j], grad_rgb + 2048, 64, w.mt, w.nt, inv_scale, g, q); break;
+            default: wgrad_flush(acc[j], grad_rgb + 2048 + 4096, 64, w.mt, w.nt, inv_scale, g, q); break;
+        }
+    }
+}
+
+extern "C" size_t ngp_net_backward_workspace(void) { return 0; }
+
+extern "C" int ngp_net_backward(const NgpNet* net, const NgpSamples* smp, const float* dL_dsigmas, const float* dL_drgbs,
+                                const void* feat_save, const float* loss_scale, float* grad_enc, float* grad_rgb,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+    (void)workspace; (void)workspace_bytes;
+    if (!net || !smp || smp->n < 0 || !dL_dsigmas || !dL_drgbs || !grad_enc || !grad_rgb) return NGP_EINVAL;
+    if (net->meta.n_levels < 1 || net->meta.n_levels > NGP_MAX_LEVELS) return NGP_EINVAL;
+    if (smp->n == 0) return 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        NGP_CUDA(cudaFuncSetAttribute(k_ngp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
+        attr_set = true;
+    }
+    const int64_t n_mtiles = (smp->n + 15) / 16;
+    const int64_t n_blks = (n_mtiles + BWD_WARPS - 1) / BWD_WARPS;
+    const int grid = (int)(n_blks < (int64_t)ngp_sm_count() ? n_blks : ngp_sm_count());
+    k_ngp_bwd<<<grid, BWD_THREADS, sizeof(BwdSmem), (cudaStream_t)stream>>>(
+        *net, *smp, dL_dsigmas, dL_drgbs, (const uint4*)feat_save, loss_scale, grad_enc, grad_rgb);
+    NGP_CHECK_LAUNCH();
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// loss-scale helper
+// -------------------------------------------------------------------------------------------------
+__global__ void k_grad_amax(const float* __restrict__ dsig, const float* __restrict__ sig, const float* __restrict__ drgb,
+                            int64_t n, float* __restrict__ amax) {
+    float m = 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float s = fminf(sig[i], 3.2690173e6f);  // exp(15): the TruncExp backward clamp
+        m = fmaxf(m, fabsf(dsig[i] * s));
+        m = fmaxf(m, fmaxf(fabsf(drgb[3 * i]), fmaxf(fabsf(drgb[3 * i + 1]), fabsf(drgb[3 * i + 2]))));
+    }
+    m = warp_max(m);
+    // non-negative floats order like their bit patterns
+    if ((threadIdx.x & 31) == 0 && m > 0.f && m < INFINITY) atomicMax(reinterpret_cast<int*>(amax), __float_as_int(m));
+}
+__global__ void k_grad_scale(float* __restrict__ amax, float* __restrict__ scale_out) {
+    const float m = *amax;
+    float s = 1.0f;
+    if (m > 0.f && m < INFINITY) {
+        int e;
+        frexpf(256.0f / m, &e);  // 256/m = f * 2^e, f in [0.5,1)  ->  2^(e-1) <= 256/m
+        e = max(-60, min(60, e - 1));
+        s = scalbnf(1.0f, e);
+    }
+    *scale_out = s;
+    *amax = 0.f;
+}
+extern "C" int ngp_grad_scale(const float* dL_dsigmas, const float* sigmas, const float* dL_drgbs, int64_t n,
+                              float* scratch, float* scale_out, void* stream) {
+    if (n < 0 || !scratch || !scale_out) return NGP_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    NGP_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float), st));
+    if (n > 0) {
+        int grid = ngp_div_up(n, 256);
+        if (grid > 4 * ngp_sm_count()) grid = 4 * ngp_sm_count();
+        k_grad_amax<<<grid, 256, 0, st>>>(dL_dsigmas, sigmas, dL_drgbs, n, scratch);
+        NGP_CHECK_LAUNCH();
+    }
+    k_grad_scale<<<1, 1, 0, st>>>(scratch, scale_out);
+    NGP_CHECK_LAUNCH();
+    return 0;
+}
