@@ -226,7 +226,7 @@ def torch_grid_encode(meta, table, x01):
         g = torch.floor(pos)
         w = pos - g
         gi = g.to(torch.int64)
-        acc = torch.zeros(n, 2, dtype=torch.float32)
+        acc = torch.zeros(n, 2, dtype=torch.float32, device=x01.device)
         for c in range(8):
             px = gi[:, 0] + (c & 1)
             py = gi[:, 1] + ((c >> 1) & 1)
@@ -239,7 +239,7 @@ def torch_grid_encode(meta, table, x01):
             acc = acc + wt[:, None] * table[off + idx]
         feats.append(_rt(acc))
     for l in range(meta.n_levels, 16):
-        feats.append(torch.zeros(n, 2))
+        feats.append(torch.zeros(n, 2, device=x01.device))
     return torch.cat(feats, 1)
 
 
