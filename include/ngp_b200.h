@@ -137,7 +137,8 @@ typedef struct {
     const float* rays_d;
     const int32_t* ray_idx;
     const float* ts;
-    int64_t n;
+    int64_t n;            /* number of samples, or the CAPACITY when n_dev is set */
+    const int32_t* n_dev; /* optional device int32: the kernels read the sample count from here (no host sync) */
 } NgpSamples;
 
 /* Fused forward of NGP.forward (networks.py:132-153): hash gather + trilinear + density MLP +
@@ -160,6 +161,112 @@ int ngp_net_backward(const NgpNet* net, const NgpSamples* smp, const float* dL_d
 /* loss_scale helper: *scale_out = 2^floor(log2(256 / max(|dL_dsigmas*sigma'|, |dL_drgbs|))) (1 if all zero). */
 int ngp_grad_scale(const float* dL_dsigmas, const float* sigmas, const float* dL_drgbs, int64_t n,
                    float* scratch /* 1 float */, float* scale_out, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * Fused training path: the body of render(..., test_time=False) (reference models/rendering.py:11-43,
+ * :121-163) without a single host synchronisation -- AABB + near clamp + march (one pass, per-ray
+ * staging) -> prefix sum -> compaction -> ngp_net_forward -> ragged compositing, and its backward.
+ * All sample counts stay on the device; every per-sample buffer is sized for `max_total_samples`
+ * (n_rays * max_samples can never overflow).
+ * -------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t n_rays, cascades, grid_size, max_samples;
+    float scale, exp_step_factor, T_threshold, near_distance;
+    float center[3], half_size[3], bg[3];
+    float lambda_opacity;      /* NeRFLoss lambda_opacity (reference losses.py:41) */
+    int64_t max_total_samples; /* capacity of the per-sample buffers */
+} NgpTrainCfg;
+
+typedef struct {
+    /* inputs */
+    const float* rays_o;          /* (n_rays,3) */
+    const float* rays_d;          /* (n_rays,3) unnormalised */
+    const float* noise;           /* (n_rays) start jitter in [0,1) */
+    const uint8_t* density_bitfield;
+    /* per-ray */
+    float* stage_t;               /* (n_rays*max_samples) marcher staging */
+    float* stage_dt;              /* (n_rays*max_samples) */
+    int32_t* n_samples;           /* (n_rays) marched samples per ray == rays_a[:,2] */
+    int32_t* offsets;             /* (n_rays) exclusive prefix sum == rays_a[:,1] */
+    int32_t* counters;            /* [0] total marched samples (rm_samples), [1] total composited (vr_samples) */
+    float* rgb;                   /* (n_rays,3) composited colour incl. background */
+    float* opacity;               /* (n_rays) */
+    float* depth;                 /* (n_rays) */
+    /* per-sample (capacity max_total_samples) */
+    int32_t* ray_idx;
+    float* ts;
+    float* deltas;
+    float* sigmas;
+    float* rgbs;                  /* (S,3) */
+    float* ws;                    /* (S) optional (NULL: not materialised) */
+    float* dsigmas;               /* (S)   backward scratch */
+    float* drgbs;                 /* (S,3) backward scratch */
+    void* feat_save;              /* ceil32(S)*64 bytes */
+    float* scalars;               /* [0] amax scratch, [1] loss scale, [2] sum sq err, [3] sum opacity entropy */
+    void* scan_temp;
+    size_t scan_temp_bytes;
+} NgpTrainBuffers;
+
+size_t ngp_train_scan_temp_bytes(int n_rays);
+
+/* forward: fills per-ray rgb/opacity/depth (+ws) and everything the backward needs */
+int ngp_render_train_fwd(const NgpNet* net, const NgpTrainCfg* cfg, const NgpTrainBuffers* buf, void* stream);
+
+/* backward from per-ray gradients (dL_ddepth / dL_dws may be NULL = 0); accumulates (+=) into the
+ * fp32 gradient vectors laid out like the parameter vectors. */
+int ngp_render_train_bwd(const NgpNet* net, const NgpTrainCfg* cfg, const NgpTrainBuffers* buf,
+                         const float* dL_drgb, const float* dL_dopacity, const float* dL_ddepth, const float* dL_dws,
+                         float* grad_enc, float* grad_rgb, void* stream);
+
+/* NeRFLoss (reference losses.py:47-60, distortion off) and its per-ray gradients, on the device:
+ * loss = mean((rgb-gt)^2) + lambda_opacity*mean(-o*log(o)), o = opacity+1e-10.
+ * Adds the two sums into buf->scalars[2], [3] (caller zeroes them) and writes dL_drgb (n,3), dL_dopacity (n). */
+int ngp_nerf_loss_grad(const NgpTrainCfg* cfg, const NgpTrainBuffers* buf, const float* rgb_gt,
+                       float* dL_drgb, float* dL_dopacity, void* stream);
+
+/* Fused Adam over a flat fp32 vector (apex FusedAdam semantics as the reference uses it, train.py:131:
+ * adam_w_mode, weight_decay 0, bias correction, eps): p -= lr * m_hat / (sqrt(v_hat) + eps), with
+ * g = grads * grad_mul (1/world_size after a sum all-reduce). Also refreshes the fp16 working copy and
+ * zeroes the gradient for the next step in the same pass. lr and step live on the device
+ * (lr_dev[0], step_dev[0] = number of completed steps; the kernel uses t = step+1 and a follow-up
+ * single-thread kernel increments it) so a captured CUDA graph never needs re-capturing. */
+int ngp_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, uint16_t* params_half, int64_t n,
+                  const float* lr_dev, int32_t* step_dev, float beta1, float beta2, float eps, float grad_mul,
+                  int increment_step, void* stream);
+
+/* Batch assembly on the device (reference train.py:78-91 + datasets/ray_utils.py:46-70 + base.py:22-30):
+ * rays_d = directions[pix] @ R^T, rays_o = c2w[:,3], rgb_gt = images[img, pix] / 255. */
+int ngp_gen_rays(const int64_t* img_idx, const int64_t* pix_idx, const float* poses /* (n_img,3,4) */,
+                 const float* directions /* (n_pix,3) */, const uint8_t* images /* (n_img,n_pix,3) or NULL */,
+                 int64_t n_pix, int n, float* rays_o, float* rays_d, float* rgb_gt, void* stream);
+
+/* Occupancy-grid refresh on the device (reference networks.py:240-269 + :169-195), no host sync:
+ * picks cells (all cells when warmup, else M uniform + M occupied per cascade), evaluates sigma at a
+ * jittered point of each, grid = grid<0 ? grid : max(grid*decay, sigma), threshold = min(mean of
+ * positive cells, density_threshold), packs the bitfield. workspace: see ngp_update_grid_workspace. */
+size_t ngp_update_grid_workspace(int cascades, int grid_size);
+int ngp_update_density_grid(const NgpNet* net, float* density_grid /* (cascades, G^3) */, uint8_t* density_bitfield,
+                            int cascades, int grid_size, float scale, float density_threshold, int warmup, float decay,
+                            uint32_t seed, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * Fused inference path: render(..., test_time=True) (reference models/rendering.py:46-118) as a
+ * device-side wavefront without host synchronisation. rays are (n_rays,3); outputs opacity, depth
+ * (n_rays), rgb (n_rays,3, background included); total_samples (device int64, optional) = the
+ * reference's result['total_samples'].
+ * -------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t n_rays, cascades, grid_size, max_samples; /* max_samples: the marcher's MAX_SAMPLES (step lower bound) */
+    float scale, exp_step_factor, T_threshold, near_distance;
+    float center[3], half_size[3], bg[3];
+    int32_t sample_budget;      /* reference kwarg `max_samples` of the outer loop (default 1024) */
+    int64_t max_round_samples;  /* capacity of the per-round sample buffers (rays that do not fit wait a round) */
+} NgpInferCfg;
+
+size_t ngp_render_infer_workspace(int n_rays, int64_t max_round_samples);
+int ngp_render_infer(const NgpNet* net, const NgpInferCfg* cfg, const float* rays_o, const float* rays_d,
+                     const uint8_t* density_bitfield, float* opacity, float* depth, float* rgb, int64_t* total_samples,
+                     void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

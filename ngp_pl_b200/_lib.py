@@ -45,6 +45,7 @@ class NgpSamples(C.Structure):
         ("ray_idx", C.c_void_p),
         ("ts", C.c_void_p),
         ("n", C.c_int64),
+        ("n_dev", C.c_void_p),
     ]
 
 
@@ -65,6 +66,34 @@ class NgpTrainCfg(C.Structure):
         ("lambda_opacity", C.c_float),
         ("max_total_samples", C.c_int64),
     ]
+
+
+class NgpInferCfg(C.Structure):
+    """Mirror of NgpInferCfg in include/ngp_b200.h."""
+    _fields_ = [
+        ("n_rays", C.c_int32),
+        ("cascades", C.c_int32),
+        ("grid_size", C.c_int32),
+        ("max_samples", C.c_int32),
+        ("scale", C.c_float),
+        ("exp_step_factor", C.c_float),
+        ("T_threshold", C.c_float),
+        ("near_distance", C.c_float),
+        ("center", C.c_float * 3),
+        ("half_size", C.c_float * 3),
+        ("bg", C.c_float * 3),
+        ("sample_budget", C.c_int32),
+        ("max_round_samples", C.c_int64),
+    ]
+
+
+class NgpTrainBuffers(C.Structure):
+    """Mirror of NgpTrainBuffers in include/ngp_b200.h."""
+    _fields_ = [(n, C.c_void_p) for n in (
+        "rays_o", "rays_d", "noise", "density_bitfield",
+        "stage_t", "stage_dt", "n_samples", "offsets", "counters", "rgb", "opacity", "depth",
+        "ray_idx", "ts", "deltas", "sigmas", "rgbs", "ws", "dsigmas", "drgbs", "feat_save", "scalars",
+        "scan_temp")] + [("scan_temp_bytes", C.c_size_t)]
 
 
 _P = C.c_void_p
@@ -96,6 +125,17 @@ SIGNATURES = {
     "ngp_net_backward_workspace": (_sz, []),
     "ngp_net_backward": (_i, [C.POINTER(NgpNet), C.POINTER(NgpSamples), _P, _P, _P, _P, _P, _P, _P, _sz, _P]),
     "ngp_grad_scale": (_i, [_P, _P, _P, _i64, _P, _P, _P]),
+    "ngp_train_scan_temp_bytes": (_sz, [_i]),
+    "ngp_render_train_fwd": (_i, [C.POINTER(NgpNet), C.POINTER(NgpTrainCfg), C.POINTER(NgpTrainBuffers), _P]),
+    "ngp_render_train_bwd": (_i, [C.POINTER(NgpNet), C.POINTER(NgpTrainCfg), C.POINTER(NgpTrainBuffers),
+                                  _P, _P, _P, _P, _P, _P, _P]),
+    "ngp_nerf_loss_grad": (_i, [C.POINTER(NgpTrainCfg), C.POINTER(NgpTrainBuffers), _P, _P, _P, _P]),
+    "ngp_adam_step": (_i, [_P, _P, _P, _P, _P, _i64, _P, _P, _f, _f, _f, _f, _i, _P]),
+    "ngp_gen_rays": (_i, [_P, _P, _P, _P, _P, _i64, _i, _P, _P, _P, _P]),
+    "ngp_render_infer_workspace": (_sz, [_i, _i64]),
+    "ngp_render_infer": (_i, [C.POINTER(NgpNet), C.POINTER(NgpInferCfg), _P, _P, _P, _P, _P, _P, _P, _P, _sz, _P]),
+    "ngp_update_grid_workspace": (_sz, [_i, _i]),
+    "ngp_update_density_grid": (_i, [C.POINTER(NgpNet), _P, _P, _i, _i, _f, _f, _i, _f, C.c_uint32, _P, _sz, _P]),
 }
 
 _lib = None

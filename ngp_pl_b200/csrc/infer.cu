@@ -1,0 +1,268 @@
+// Sync-free inference render for sm_100a: what render(test_time=True) does (reference
+// models/rendering.py:46-118) as a device-side wavefront.
+//
+// The reference loops on the host: march N more samples for every alive ray, evaluate the network,
+// composite, drop converged rays (boolean-mask compaction => >= 3 host syncs per round, tens of rounds
+// per image). Here the alive list, the per-round sample counts and the convergence test all stay on
+// the device: the host enqueues a FIXED schedule of rounds (2,2,4,4,...,64,64,... samples per ray per
+// round) and late rounds simply find an empty alive list. Each ray still sees exactly the reference's
+// sample sequence (raymarching_test_kernel semantics, incl. its `cascades`-as-scale quirk) and the same
+// front-to-back accumulation order, so results differ from the reference only by the fp16-level network
+// difference and by where the chunk boundaries fall (T is resumed as 1 - opacity, volumerendering.cu:230).
+#include "common.cuh"
+#include "march.cuh"
+#include "../../include/ngp_b200.h"
+
+#define INFER_MAX_ROUNDS 64
+
+// init: AABB (+ near clamp), zero the accumulators, build the first alive list
+__global__ void k_infer_init(const NgpInferCfg cfg, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                             float* __restrict__ t_cur, float* __restrict__ t_end, float* __restrict__ opacity,
+                             float* __restrict__ depth, float* __restrict__ rgb, int* __restrict__ alive,
+                             int* __restrict__ alive_count) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool hit = false;
+    if (r < cfg.n_rays) {
+        const MarchRay ray = make_march_ray(rays_o[3 * r], rays_o[3 * r + 1], rays_o[3 * r + 2],
+                                            rays_d[3 * r], rays_d[3 * r + 1], rays_d[3 * r + 2]);
+        const float2 tt = ray_aabb(ray, cfg.center[0], cfg.center[1], cfg.center[2], cfg.half_size[0], cfg.half_size[1],
+                                   cfg.half_size[2]);
+        float t1 = -1.0f, t2 = -1.0f;
+        if (tt.y > 0.0f) {
+            t1 = fmaxf(tt.x, 0.0f);
+            t2 = tt.y;
+        }
+        if (t1 >= 0.0f && t1 < cfg.near_distance) t1 = cfg.near_distance;
+        t_cur[r] = t1;
+        t_end[r] = t2;
+        opacity[r] = 0.f;
+        depth[r] = 0.f;
+        rgb[3 * r] = 0.f; rgb[3 * r + 1] = 0.f; rgb[3 * r + 2] = 0.f;
+        hit = t1 >= 0.0f && t1 < t2;
+    }
+    // warp-aggregated append
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (m) {
+        int base = 0;
+        const int leader = __ffs(m) - 1;
+        if (lane == leader) base = atomicAdd(alive_count, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (hit) alive[base + __popc(m & ((1u << lane) - 1u))] = r;
+    }
+}
+
+// one round of marching: every alive ray takes up to S occupied samples (staged in shared memory),
+// then the warp claims a contiguous range of the compact sample arrays with one atomic.
+__global__ void k_infer_march(const NgpInferCfg cfg, const int S, const float* __restrict__ rays_o,
+                              const float* __restrict__ rays_d, const uint8_t* __restrict__ bitfield,
+                              float* __restrict__ t_cur, const float* __restrict__ t_end, const int* __restrict__ alive,
+                              const int* __restrict__ alive_count, int* __restrict__ ray_start, int* __restrict__ ray_n,
+                              int* __restrict__ ray_idx, float* __restrict__ ts, float* __restrict__ deltas,
+                              int* __restrict__ sample_count) {
+    extern __shared__ float2 stage[];  // [blockDim.x][S]
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int n_alive = *alive_count;
+    if ((int)(blockIdx.x * blockDim.x) >= n_alive) return;
+    float2* my = stage + (size_t)threadIdx.x * S;
+    int n = 0, r = -1;
+    float t = 0.f;
+    if (i < n_alive) {
+        r = alive[i];
+        const MarchConst c = make_march_const(bitfield, cfg.cascades, cfg.grid_size, cfg.max_samples, cfg.scale,
+                                              cfg.exp_step_factor, (float)cfg.cascades);
+        const MarchRay ray = make_march_ray(rays_o[3 * r], rays_o[3 * r + 1], rays_o[3 * r + 2],
+                                            rays_d[3 * r], rays_d[3 * r + 1], rays_d[3 * r + 2]);
+        t = t_cur[r];
+        const float t2 = t_end[r];
+        float x, y, z, dt;
+        while (t < t2 && n < S) {
+            if (march_visit(ray, c, t, x, y, z, dt)) {
+                my[n] = make_float2(t, dt);
+                t = __fadd_rn(t, dt);
+                ++n;
+            }
+        }
+    }
+    // inclusive prefix of the counts across the warp, one atomic per warp
+    int pre = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, pre, o);
+        if (lane >= o) pre += u;
+    }
+    const int warp_total = __shfl_sync(0xffffffffu, pre, 31);
+    int base = 0;
+    if (lane == 31 && warp_total > 0) base = atomicAdd(sample_count, warp_total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (r < 0) return;
+    int start = base + pre - n;
+    // capacity clamp: a ray that does not fit keeps its samples for the next round (t_cur not advanced)
+    if ((int64_t)start + n > cfg.max_round_samples) {
+        n = (int)max((int64_t)0, cfg.max_round_samples - start);
+        t = n > 0 ? __fadd_rn(my[n - 1].x, my[n - 1].y) : t_cur[r];
+    }
+    ray_start[i] = start;
+    ray_n[i] = n;
+    t_cur[r] = t;
+    for (int k = 0; k < n; ++k) {
+        ray_idx[start + k] = r;
+        ts[start + k] = my[k].x;
+        deltas[start + k] = my[k].y;
+    }
+}
+
+// clamp the claimed sample count to the capacity (the network kernel reads it as its `n`)
+__global__ void k_infer_clamp(int* __restrict__ sample_count, int64_t cap, int64_t* __restrict__ total) {
+    int v = *sample_count;
+    if (v > cap) v = (int)cap;
+    *sample_count = v;
+    *total += v;
+}
+
+// composite this round's samples of every alive ray (one thread per ray, <= 64 samples, same serial
+// order as the reference's composite_test_fw_kernel) and append the survivors to the next alive list
+__global__ void k_infer_composite(const NgpInferCfg cfg, const int S, const float* __restrict__ sigmas,
+                                  const float* __restrict__ rgbs, const float* __restrict__ deltas,
+                                  const float* __restrict__ ts, const int* __restrict__ ray_start,
+                                  const int* __restrict__ ray_n, const float* __restrict__ t_cur,
+                                  const float* __restrict__ t_end, const int* __restrict__ alive,
+                                  const int* __restrict__ alive_count, float* __restrict__ opacity,
+                                  float* __restrict__ depth, float* __restrict__ rgb, int* __restrict__ next_alive,
+                                  int* __restrict__ next_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int n_alive = *alive_count;
+    if ((int)(blockIdx.x * blockDim.x) >= n_alive) return;
+    bool keep = false;
+    int r = -1;
+    if (i < n_alive) {
+        r = alive[i];
+        const int n = ray_n[i];
+        const int start = ray_start[i];
+        float o = opacity[r], d = depth[r];
+        float cr = rgb[3 * r], cg = rgb[3 * r + 1], cb = rgb[3 * r + 2];
+        float T = 1.0f - o;
+        bool term = false;
+        for (int s = 0; s < n; ++s) {
+            const int k = start + s;
+            const float a = 1.0f - __expf(-(__ldg(sigmas + k) * __ldg(deltas + k)));
+            const float w = a * T;
+            cr = fmaf(w, __ldg(rgbs + 3 * k), cr);
+            cg = fmaf(w, __ldg(rgbs + 3 * k + 1), cg);
+            cb = fmaf(w, __ldg(rgbs + 3 * k + 2), cb);
+            d = fmaf(w, __ldg(ts + k), d);
+            o += w;
+            T *= 1.0f - a;
+            if (T <= cfg.T_threshold) {
+                term = true;
+                break;
+            }
+        }
+        opacity[r] = o;
+        depth[r] = d;
+        rgb[3 * r] = cr; rgb[3 * r + 1] = cg; rgb[3 * r + 2] = cb;
+        // alive while not converged and still inside the box
+        keep = !term && (t_cur[r] < t_end[r]);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (m) {
+        int base = 0;
+        const int leader = __ffs(m) - 1;
+        if (lane == leader) base = atomicAdd(next_count, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (keep) next_alive[base + __popc(m & ((1u << lane) - 1u))] = r;
+    }
+}
+
+__global__ void k_infer_finish(const NgpInferCfg cfg, const float* __restrict__ opacity, float* __restrict__ rgb) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= cfg.n_rays) return;
+    const float rest = 1.0f - opacity[r];  // reference rendering.py:112-116
+    rgb[3 * r] += cfg.bg[0] * rest;
+    rgb[3 * r + 1] += cfg.bg[1] * rest;
+    rgb[3 * r + 2] += cfg.bg[2] * rest;
+}
+
+static int round_samples(int round) {
+    // 2,2,4,4,8,8,16,16,32,32,64,64,...
+    const int e = 1 + round / 2;
+    return e >= 6 ? 64 : (1 << e);
+}
+
+extern "C" size_t ngp_render_infer_workspace(int n_rays, int64_t max_round_samples) {
+    if (n_rays < 1 || max_round_samples < 1) return 0;
+    const size_t nr = ((size_t)n_rays * 4 + 255) & ~(size_t)255;
+    const size_t ns = ((size_t)max_round_samples * 4 + 255) & ~(size_t)255;
+    // t_cur, t_end, alive[2], ray_start, ray_n  |  ray_idx, ts, deltas, sigmas, rgbs(3)  |  counters
+    return 6 * nr + 7 * ns + 4096;
+}
+
+extern "C" int ngp_render_infer(const NgpNet* net, const NgpInferCfg* cfg, const float* rays_o, const float* rays_d,
+                                const uint8_t* density_bitfield, float* opacity, float* depth, float* rgb,
+                                int64_t* total_samples, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!net || !cfg || !rays_o || !rays_d || !density_bitfield || !opacity || !depth || !rgb || !workspace) return NGP_EINVAL;
+    if (cfg->n_rays < 1 || cfg->cascades < 1 || cfg->grid_size < 1 || cfg->grid_size > 1024 || cfg->max_samples < 1 ||
+        cfg->max_round_samples < 64 || cfg->max_round_samples > 0x7fffffffll || cfg->sample_budget < 1)
+        return NGP_EINVAL;
+    if (workspace_bytes < ngp_render_infer_workspace(cfg->n_rays, cfg->max_round_samples)) return NGP_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = cfg->n_rays;
+    const size_t nr = ((size_t)n * 4 + 255) & ~(size_t)255;
+    const size_t ns = ((size_t)cfg->max_round_samples * 4 + 255) & ~(size_t)255;
+    char* w = (char*)workspace;
+    float* t_cur = (float*)w; w += nr;
+    float* t_end = (float*)w; w += nr;
+    int* alive[2];
+    alive[0] = (int*)w; w += nr;
+    alive[1] = (int*)w; w += nr;
+    int* ray_start = (int*)w; w += nr;
+    int* ray_n = (int*)w; w += nr;
+    int* ray_idx = (int*)w; w += ns;
+    float* ts = (float*)w; w += ns;
+    float* deltas = (float*)w; w += ns;
+    float* sigmas = (float*)w; w += ns;
+    float* rgbs = (float*)w; w += 3 * ns;
+    int* counters = (int*)w;  // [0..64] alive counts per round, [128..191] sample counts per round, [256..257] int64 total
+    int* alive_cnt = counters;
+    int* sample_cnt = counters + 128;
+    int64_t* total = (int64_t*)(counters + 256);
+    NGP_CUDA(cudaMemsetAsync(counters, 0, 4096, st));
+
+    k_infer_init<<<ngp_div_up(n, 256), 256, 0, st>>>(*cfg, rays_o, rays_d, t_cur, t_end, opacity, depth, rgb, alive[0],
+                                                      alive_cnt);
+    NGP_CHECK_LAUNCH();
+    static bool attr_set = false;
+    if (!attr_set) {
+        NGP_CUDA(cudaFuncSetAttribute(k_infer_march, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 64 * 8));
+        attr_set = true;
+    }
+    int requested = 0;
+    for (int round = 0; round < INFER_MAX_ROUNDS && requested < cfg->sample_budget; ++round) {
+        const int S = round_samples(round);
+        requested += S;
+        const int bs = 64;
+        // the launch covers the worst case (all rays alive); blocks past the device-side count exit at once
+        const int grid = ngp_div_up(n, bs);
+        k_infer_march<<<grid, bs, (size_t)bs * S * sizeof(float2), st>>>(
+            *cfg, S, rays_o, rays_d, density_bitfield, t_cur, t_end, alive[round & 1], alive_cnt + round, ray_start, ray_n,
+            ray_idx, ts, deltas, sample_cnt + round);
+        NGP_CHECK_LAUNCH();
+        k_infer_clamp<<<1, 1, 0, st>>>(sample_cnt + round, cfg->max_round_samples, total);
+        NGP_CHECK_LAUNCH();
+        NgpSamples smp;
+        smp.xyzs = nullptr; smp.dirs = nullptr; smp.rays_o = rays_o; smp.rays_d = rays_d; smp.ray_idx = ray_idx; smp.ts = ts;
+        smp.n = cfg->max_round_samples; smp.n_dev = sample_cnt + round;
+        int rc = ngp_net_forward(net, &smp, 1, sigmas, rgbs, nullptr, nullptr, stream);
+        if (rc) return rc;
+        k_infer_composite<<<grid, bs, 0, st>>>(*cfg, S, sigmas, rgbs, deltas, ts, ray_start, ray_n, t_cur, t_end,
+                                                alive[round & 1], alive_cnt + round, opacity, depth, rgb,
+                                                alive[(round + 1) & 1], alive_cnt + round + 1);
+        NGP_CHECK_LAUNCH();
+    }
+    k_infer_finish<<<ngp_div_up(n, 256), 256, 0, st>>>(*cfg, opacity, rgb);
+    NGP_CHECK_LAUNCH();
+    if (total_samples) NGP_CUDA(cudaMemcpyAsync(total_samples, total, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}

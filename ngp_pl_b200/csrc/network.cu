@@ -74,6 +74,15 @@ struct SampleIn {
     float x, y, z;     // world position
     float dx, dy, dz;  // (unnormalised) view direction
 };
+// number of live samples: from the device counter when one is given (clamped to the capacity)
+__device__ __forceinline__ int64_t sample_count(const NgpSamples& s) {
+    if (s.n_dev) {
+        const int64_t v = (int64_t)__ldg(s.n_dev);
+        return v < s.n ? (v < 0 ? 0 : v) : s.n;
+    }
+    return s.n;
+}
+
 __device__ __forceinline__ SampleIn load_sample(const NgpSamples& s, int64_t i, bool valid) {
     SampleIn o;
     if (!valid) {
@@ -161,7 +170,7 @@ k_ngp_fwd(const NgpNet net, const NgpSamples smp, const int want_rgb, float* __r
     const uint32_t* table = reinterpret_cast<const uint32_t*>(wd + NGP_DENSITY_MLP_PARAMS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
-    const int64_t n = smp.n;
+    const int64_t n = sample_count(smp);
     const int64_t n_tiles = (n + 16 * FWD_MT - 1) / (16 * FWD_MT);
     const int warps_per_cta = FWD_THREADS / 32;
 
@@ -374,7 +383,7 @@ k_ngp_bwd(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_d
     float* grad_table = grad_enc + NGP_DENSITY_MLP_PARAMS;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
-    const int64_t n = smp.n;
+    const int64_t n = sample_count(smp);
     const int64_t n_mtiles = (n + 15) / 16;
     const int64_t n_blks = (n_mtiles + BWD_WARPS - 1) / BWD_WARPS;
     const float scale = loss_scale ? *loss_scale : 1.0f;

@@ -1,0 +1,558 @@
+// Fused training path for sm_100a: everything render(test_time=False) does (reference
+// models/rendering.py:11-43,:121-163) plus loss, optimiser, batch assembly and the occupancy-grid
+// refresh, as a handful of stream-ordered launches with NO host synchronisation (sample counts never
+// leave the device), so a whole optimiser step can be captured in one CUDA graph.
+#include "common.cuh"
+#include "march.cuh"
+#include "composite.cuh"
+#include "../../include/ngp_b200.h"
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+
+static inline int one_thread_per_ray_block(int n_rays) { return n_rays >= 148 * 128 * 4 ? 128 : 32; }
+
+// -------------------------------------------------------------------------------------------------
+// 1. AABB + near clamp + jittered march, ONE pass: samples go to a per-ray staging row
+//    (reference intersection.cu:25-56, rendering.py:29, raymarching.cu:166-235)
+// -------------------------------------------------------------------------------------------------
+__global__ void k_train_march(const NgpTrainCfg cfg, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                              const float* __restrict__ noise, const uint8_t* __restrict__ bitfield,
+                              float* __restrict__ stage_t, float* __restrict__ stage_dt, int* __restrict__ n_samples) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= cfg.n_rays) return;
+    const MarchConst c = make_march_const(bitfield, cfg.cascades, cfg.grid_size, cfg.max_samples, cfg.scale,
+                                          cfg.exp_step_factor, cfg.scale);
+    const MarchRay ray = make_march_ray(rays_o[3 * r], rays_o[3 * r + 1], rays_o[3 * r + 2],
+                                        rays_d[3 * r], rays_d[3 * r + 1], rays_d[3 * r + 2]);
+    const float2 tt = ray_aabb(ray, cfg.center[0], cfg.center[1], cfg.center[2], cfg.half_size[0], cfg.half_size[1],
+                               cfg.half_size[2]);
+    float t1 = -1.0f, t2 = -1.0f;
+    if (tt.y > 0.0f) {
+        t1 = fmaxf(tt.x, 0.0f);
+        t2 = tt.y;
+    }
+    if (t1 >= 0.0f && t1 < cfg.near_distance) t1 = cfg.near_distance;
+    float t = march_jitter(t1, noise[r], c);
+    int n = 0;
+    float x, y, z, dt;
+    float* st = stage_t + (size_t)r * cfg.max_samples;
+    float* sd = stage_dt + (size_t)r * cfg.max_samples;
+    while (0.0f <= t && t < t2 && n < cfg.max_samples) {
+        if (march_visit(ray, c, t, x, y, z, dt)) {
+            st[n] = t;
+            sd[n] = dt;
+            t = __fadd_rn(t, dt);
+            ++n;
+        }
+    }
+    n_samples[r] = n;
+}
+
+// 3. staging rows -> compact per-sample arrays (one warp per ray, coalesced both ways)
+__global__ void k_train_compact(const NgpTrainCfg cfg, const float* __restrict__ stage_t, const float* __restrict__ stage_dt,
+                                const int* __restrict__ n_samples, const int* __restrict__ offsets,
+                                int* __restrict__ ray_idx, float* __restrict__ ts, float* __restrict__ deltas,
+                                int* __restrict__ counters) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= cfg.n_rays) return;
+    const int n = n_samples[w];
+    const int64_t start = offsets[w];
+    if (w == cfg.n_rays - 1 && lane == 0) {
+        int64_t tot = start + n;
+        counters[0] = (int)(tot < cfg.max_total_samples ? tot : cfg.max_total_samples);
+        counters[1] = 0;
+    }
+    const float* st = stage_t + (size_t)w * cfg.max_samples;
+    const float* sd = stage_dt + (size_t)w * cfg.max_samples;
+    for (int i = lane; i < n; i += 32) {
+        const int64_t s = start + i;
+        if (s < cfg.max_total_samples) {
+            ray_idx[s] = w;
+            ts[s] = st[i];
+            deltas[s] = sd[i];
+        }
+    }
+}
+
+// 5. ragged compositing of the network outputs, one warp per ray, + background
+__global__ void k_train_composite_fw(const NgpTrainCfg cfg, const int* __restrict__ n_samples, const int* __restrict__ offsets,
+                                     const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                     const float* __restrict__ deltas, const float* __restrict__ ts,
+                                     float* __restrict__ rgb, float* __restrict__ opacity, float* __restrict__ depth,
+                                     float* __restrict__ ws, int* __restrict__ counters) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= cfg.n_rays) return;
+    const int64_t start = offsets[w];
+    int n = n_samples[w];
+    if (start + n > cfg.max_total_samples) n = (int)max((int64_t)0, cfg.max_total_samples - start);
+    const float* sg = sigmas + start;
+    const float* dl = deltas + start;
+    const float* tt = ts + start;
+    const float* cl = rgbs + 3 * start;
+    float* wo = ws ? ws + start : nullptr;
+    const CompositeOut o = composite_ray_warp(
+        n, cfg.T_threshold, lane,
+        [&](int i) { return __ldg(sg + i); }, [&](int i) { return __ldg(dl + i); }, [&](int i) { return __ldg(tt + i); },
+        [&](int i) { return make_float3(__ldg(cl + 3 * i), __ldg(cl + 3 * i + 1), __ldg(cl + 3 * i + 2)); },
+        [&](int i, float v) { if (wo) wo[i] = v; });
+    if (lane == 0) {
+        const float rest = 1.0f - o.opacity;  // rgb += bg * (1 - opacity), reference rendering.py:160-161
+        opacity[w] = o.opacity;
+        depth[w] = o.depth;
+        rgb[3 * w] = o.r + cfg.bg[0] * rest;
+        rgb[3 * w + 1] = o.g + cfg.bg[1] * rest;
+        rgb[3 * w + 2] = o.b + cfg.bg[2] * rest;
+        if (o.total_samples) atomicAdd(&counters[1], o.total_samples);
+    }
+}
+
+extern "C" size_t ngp_train_scan_temp_bytes(int n_rays) {
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const int*)nullptr, (int*)nullptr, n_rays > 0 ? n_rays : 1);
+    return (bytes + 255) & ~(size_t)255;
+}
+
+static NgpSamples train_samples(const NgpTrainCfg* cfg, const NgpTrainBuffers* b) {
+    NgpSamples s;
+    s.xyzs = nullptr; s.dirs = nullptr;
+    s.rays_o = b->rays_o; s.rays_d = b->rays_d;
+    s.ray_idx = b->ray_idx; s.ts = b->ts;
+    s.n = cfg->max_total_samples;
+    s.n_dev = b->counters;
+    return s;
+}
+
+static int check_train_args(const NgpNet* net, const NgpTrainCfg* cfg, const NgpTrainBuffers* b) {
+    if (!net || !cfg || !b) return NGP_EINVAL;
+    if (cfg->n_rays < 1 || cfg->cascades < 1 || cfg->grid_size < 1 || cfg->grid_size > 1024 || cfg->max_samples < 1 ||
+        cfg->max_total_samples < 1 || cfg->max_total_samples > 0x7fffffffll)
+        return NGP_EINVAL;
+    if (!b->rays_o || !b->rays_d || !b->noise || !b->density_bitfield || !b->stage_t || !b->stage_dt || !b->n_samples ||
+        !b->offsets || !b->counters || !b->rgb || !b->opacity || !b->depth || !b->ray_idx || !b->ts || !b->deltas ||
+        !b->sigmas || !b->rgbs || !b->scalars || !b->scan_temp)
+        return NGP_EINVAL;
+    return 0;
+}
+
+extern "C" int ngp_render_train_fwd(const NgpNet* net, const NgpTrainCfg* cfg, const NgpTrainBuffers* b, void* stream) {
+    int rc = check_train_args(net, cfg, b);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = cfg->n_rays;
+    const int bs = one_thread_per_ray_block(n);
+    k_train_march<<<ngp_div_up(n, bs), bs, 0, st>>>(*cfg, b->rays_o, b->rays_d, b->noise, b->density_bitfield, b->stage_t,
+                                                     b->stage_dt, b->n_samples);
+    NGP_CHECK_LAUNCH();
+    size_t temp_bytes = b->scan_temp_bytes;
+    NGP_CUDA(cub::DeviceScan::ExclusiveSum(b->scan_temp, temp_bytes, b->n_samples, b->offsets, n, st));
+    k_train_compact<<<ngp_div_up((int64_t)n * 32, 256), 256, 0, st>>>(*cfg, b->stage_t, b->stage_dt, b->n_samples, b->offsets,
+                                                                       b->ray_idx, b->ts, b->deltas, b->counters);
+    NGP_CHECK_LAUNCH();
+    const NgpSamples smp = train_samples(cfg, b);
+    rc = ngp_net_forward(net, &smp, 1, b->sigmas, b->rgbs, nullptr, b->feat_save, stream);
+    if (rc) return rc;
+    k_train_composite_fw<<<ngp_div_up((int64_t)n * 32, 128), 128, 0, st>>>(*cfg, b->n_samples, b->offsets, b->sigmas, b->rgbs,
+                                                                            b->deltas, b->ts, b->rgb, b->opacity, b->depth,
+                                                                            b->ws, b->counters);
+    NGP_CHECK_LAUNCH();
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// backward: compositing backward per ray (+ running max for the fp16 loss scale), then the network
+// -------------------------------------------------------------------------------------------------
+__global__ void k_train_composite_bw(const NgpTrainCfg cfg, const int* __restrict__ n_samples, const int* __restrict__ offsets,
+                                     const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                     const float* __restrict__ deltas, const float* __restrict__ ts,
+                                     const float* __restrict__ ws, const float* __restrict__ rgb,
+                                     const float* __restrict__ opacity, const float* __restrict__ depth,
+                                     const float* __restrict__ dL_drgb, const float* __restrict__ dL_dopacity,
+                                     const float* __restrict__ dL_ddepth, const float* __restrict__ dL_dws,
+                                     float* __restrict__ dsigmas, float* __restrict__ drgbs, float* __restrict__ amax) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= cfg.n_rays) return;
+    const int64_t start = offsets[w];
+    int n = n_samples[w];
+    if (start + n > cfg.max_total_samples) n = (int)max((int64_t)0, cfg.max_total_samples - start);
+    if (n == 0) return;
+    const float* sg = sigmas + start;
+    const float* dl = deltas + start;
+    const float* tt = ts + start;
+    const float* cl = rgbs + 3 * start;
+    const float* wv = ws ? ws + start : nullptr;
+    const float* dw = dL_dws ? dL_dws + start : nullptr;
+    float* ds = dsigmas + start;
+    float* dc = drgbs + 3 * start;
+    const float3 dC = make_float3(dL_drgb[3 * w], dL_drgb[3 * w + 1], dL_drgb[3 * w + 2]);
+    // the forward output is acc + bg*(1-O): undo the background to get the accumulated colour, and
+    // route its gradient into the opacity gradient
+    const float O = opacity[w];
+    const float rest = 1.0f - O;
+    const float3 C = make_float3(rgb[3 * w] - cfg.bg[0] * rest, rgb[3 * w + 1] - cfg.bg[1] * rest, rgb[3 * w + 2] - cfg.bg[2] * rest);
+    const float dO = dL_dopacity[w] - (dC.x * cfg.bg[0] + dC.y * cfg.bg[1] + dC.z * cfg.bg[2]);
+    const float dD = dL_ddepth ? dL_ddepth[w] : 0.f;
+    float m = 0.f;
+    composite_ray_warp_bwd(
+        n, cfg.T_threshold, lane, dO, dD, dC, O, depth[w], C,
+        [&](int i) { return __ldg(sg + i); }, [&](int i) { return __ldg(dl + i); }, [&](int i) { return __ldg(tt + i); },
+        [&](int i) { return make_float3(__ldg(cl + 3 * i), __ldg(cl + 3 * i + 1), __ldg(cl + 3 * i + 2)); },
+        [&](int i) { return dw ? __ldg(dw + i) : 0.f; }, [&](int i) { return (dw && wv) ? __ldg(wv + i) : 0.f; },
+        [&](int i, float v) {
+            ds[i] = v;
+            m = fmaxf(m, fabsf(v * fminf(__ldg(sg + i), 3.2690173e6f)));
+        },
+        [&](int i, float3 v) {
+            dc[3 * i] = v.x; dc[3 * i + 1] = v.y; dc[3 * i + 2] = v.z;
+            m = fmaxf(m, fmaxf(fabsf(v.x), fmaxf(fabsf(v.y), fabsf(v.z))));
+        });
+    m = warp_max(m);
+    if (lane == 0 && m > 0.f && m < INFINITY) atomicMax(reinterpret_cast<int*>(amax), __float_as_int(m));
+}
+
+__global__ void k_train_grad_scale(float* __restrict__ scalars) {
+    const float m = scalars[0];
+    float s = 1.0f;
+    if (m > 0.f && m < INFINITY) {
+        int e;
+        frexpf(256.0f / m, &e);
+        e = max(-60, min(60, e - 1));
+        s = scalbnf(1.0f, e);
+    }
+    scalars[1] = s;
+    scalars[0] = 0.f;
+}
+
+extern "C" int ngp_render_train_bwd(const NgpNet* net, const NgpTrainCfg* cfg, const NgpTrainBuffers* b,
+                                    const float* dL_drgb, const float* dL_dopacity, const float* dL_ddepth,
+                                    const float* dL_dws, float* grad_enc, float* grad_rgb, void* stream) {
+    int rc = check_train_args(net, cfg, b);
+    if (rc) return rc;
+    if (!dL_drgb || !dL_dopacity || !b->dsigmas || !b->drgbs || !grad_enc || !grad_rgb) return NGP_EINVAL;
+    if (dL_dws && !b->ws) return NGP_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = cfg->n_rays;
+    k_train_composite_bw<<<ngp_div_up((int64_t)n * 32, 128), 128, 0, st>>>(
+        *cfg, b->n_samples, b->offsets, b->sigmas, b->rgbs, b->deltas, b->ts, b->ws, b->rgb, b->opacity, b->depth, dL_drgb,
+        dL_dopacity, dL_ddepth, dL_dws, b->dsigmas, b->drgbs, b->scalars);
+    NGP_CHECK_LAUNCH();
+    k_train_grad_scale<<<1, 1, 0, st>>>(b->scalars);
+    NGP_CHECK_LAUNCH();
+    const NgpSamples smp = train_samples(cfg, b);
+    return ngp_net_backward(net, &smp, b->dsigmas, b->drgbs, b->feat_save, b->scalars + 1, grad_enc, grad_rgb, nullptr, 0,
+                            stream);
+}
+
+// -------------------------------------------------------------------------------------------------
+// NeRFLoss and its per-ray gradients (reference losses.py:47-60 with lambda_distortion = 0)
+// -------------------------------------------------------------------------------------------------
+__global__ void k_nerf_loss_grad(const NgpTrainCfg cfg, const float* __restrict__ rgb, const float* __restrict__ opacity,
+                                 const float* __restrict__ rgb_gt, float* __restrict__ dL_drgb, float* __restrict__ dL_dopacity,
+                                 float* __restrict__ scalars) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    float se = 0.f, ent = 0.f;
+    if (r < cfg.n_rays) {
+        const float inv_n = 1.0f / (float)cfg.n_rays;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float e = rgb[3 * r + c] - rgb_gt[3 * r + c];
+            se += e * e;
+            dL_drgb[3 * r + c] = 2.0f * e * inv_n * (1.0f / 3.0f);
+        }
+        const float o = opacity[r] + 1e-10f;
+        const float lg = logf(o);
+        ent = -o * lg;
+        dL_dopacity[r] = cfg.lambda_opacity * (-lg - 1.0f) * inv_n;
+    }
+    se = warp_sum(se);
+    ent = warp_sum(ent);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&scalars[2], se);
+        atomicAdd(&scalars[3], ent);
+    }
+}
+
+extern "C" int ngp_nerf_loss_grad(const NgpTrainCfg* cfg, const NgpTrainBuffers* b, const float* rgb_gt, float* dL_drgb,
+                                  float* dL_dopacity, void* stream) {
+    if (!cfg || !b || !rgb_gt || !dL_drgb || !dL_dopacity || cfg->n_rays < 1) return NGP_EINVAL;
+    k_nerf_loss_grad<<<ngp_div_up(cfg->n_rays, 256), 256, 0, (cudaStream_t)stream>>>(*cfg, b->rgb, b->opacity, rgb_gt, dL_drgb,
+                                                                                      dL_dopacity, b->scalars);
+    NGP_CHECK_LAUNCH();
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// fused Adam (+ fp16 re-cast + gradient zeroing), 128-bit accesses
+// -------------------------------------------------------------------------------------------------
+__global__ void k_adam(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                       __half* __restrict__ ph, int64_t n, const float* __restrict__ lr_dev, const int* __restrict__ step_dev,
+                       float beta1, float beta2, float eps, float grad_mul) {
+    const int t = *step_dev + 1;
+    const float lr = *lr_dev;
+    const float bc1 = 1.0f - powf(beta1, (float)t);
+    const float bc2 = 1.0f - powf(beta2, (float)t);
+    const float step_size = lr / bc1;
+    const float inv_sqrt_bc2 = rsqrtf(bc2);
+    const int64_t n4 = n >> 2;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 pv = reinterpret_cast<float4*>(p)[i];
+        float4 gv = reinterpret_cast<float4*>(g)[i];
+        float4 mv = reinterpret_cast<float4*>(m)[i];
+        float4 vv = reinterpret_cast<float4*>(v)[i];
+        float* pp = &pv.x; float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gr = gp[k] * grad_mul;
+            mp[k] = beta1 * mp[k] + (1.0f - beta1) * gr;
+            vp[k] = beta2 * vp[k] + (1.0f - beta2) * gr * gr;
+            const float denom = sqrtf(vp[k]) * inv_sqrt_bc2 + eps;
+            pp[k] -= step_size * (mp[k] / denom);
+        }
+        reinterpret_cast<float4*>(p)[i] = pv;
+        reinterpret_cast<float4*>(m)[i] = mv;
+        reinterpret_cast<float4*>(v)[i] = vv;
+        reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ph) {
+            uint2 h;
+            h.x = pack_half2(pv.x, pv.y);
+            h.y = pack_half2(pv.z, pv.w);
+            reinterpret_cast<uint2*>(ph)[i] = h;
+        }
+    }
+    // tail
+    for (int64_t i = (n4 << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float gr = g[i] * grad_mul;
+        m[i] = beta1 * m[i] + (1.0f - beta1) * gr;
+        v[i] = beta2 * v[i] + (1.0f - beta2) * gr * gr;
+        p[i] -= step_size * (m[i] / (sqrtf(v[i]) * inv_sqrt_bc2 + eps));
+        g[i] = 0.f;
+        if (ph) ph[i] = __float2half_rn(p[i]);
+    }
+}
+__global__ void k_step_inc(int* step) { *step += 1; }
+
+extern "C" int ngp_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, uint16_t* params_half, int64_t n,
+                             const float* lr_dev, int32_t* step_dev, float beta1, float beta2, float eps, float grad_mul,
+                             int increment_step, void* stream) {
+    if (!params || !grads || !exp_avg || !exp_avg_sq || !lr_dev || !step_dev || n < 0) return NGP_EINVAL;
+    if ((((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) || (((uintptr_t)params_half) & 7))
+        return NGP_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n > 0) {
+        int grid = ngp_div_up((n >> 2) + 1, 256);
+        const int cap = ngp_sm_count() * 8;
+        if (grid > cap) grid = cap;
+        k_adam<<<grid, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, (__half*)params_half, n, lr_dev, step_dev, beta1, beta2,
+                                      eps, grad_mul);
+        NGP_CHECK_LAUNCH();
+    }
+    if (increment_step) {
+        k_step_inc<<<1, 1, 0, st>>>(step_dev);
+        NGP_CHECK_LAUNCH();
+    }
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// batch assembly (reference train.py:78-91, datasets/ray_utils.py:46-70)
+// -------------------------------------------------------------------------------------------------
+__global__ void k_gen_rays(const int64_t* __restrict__ img_idx, const int64_t* __restrict__ pix_idx,
+                           const float* __restrict__ poses, const float* __restrict__ directions,
+                           const uint8_t* __restrict__ images, int64_t n_pix, int n, float* __restrict__ rays_o,
+                           float* __restrict__ rays_d, float* __restrict__ rgb_gt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t im = img_idx[i], px = pix_idx[i];
+    const float* P = poses + 12 * im;
+    const float dx = directions[3 * px], dy = directions[3 * px + 1], dz = directions[3 * px + 2];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        // rays_d = directions @ R^T  ->  d_k = sum_c dir_c * R[k][c]
+        rays_d[3 * i + k] = fmaf(dz, P[4 * k + 2], fmaf(dy, P[4 * k + 1], dx * P[4 * k]));
+        rays_o[3 * i + k] = P[4 * k + 3];
+    }
+    if (images && rgb_gt) {
+        const uint8_t* c = images + 3 * (im * n_pix + px);
+        rgb_gt[3 * i] = c[0] * (1.0f / 255.0f);
+        rgb_gt[3 * i + 1] = c[1] * (1.0f / 255.0f);
+        rgb_gt[3 * i + 2] = c[2] * (1.0f / 255.0f);
+    }
+}
+
+extern "C" int ngp_gen_rays(const int64_t* img_idx, const int64_t* pix_idx, const float* poses, const float* directions,
+                            const uint8_t* images, int64_t n_pix, int n, float* rays_o, float* rays_d, float* rgb_gt,
+                            void* stream) {
+    if (n < 0 || !img_idx || !pix_idx || !poses || !directions || !rays_o || !rays_d) return NGP_EINVAL;
+    if (n == 0) return 0;
+    k_gen_rays<<<ngp_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(img_idx, pix_idx, poses, directions, images, n_pix, n,
+                                                                      rays_o, rays_d, rgb_gt);
+    NGP_CHECK_LAUNCH();
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// occupancy-grid refresh on the device (reference networks.py:169-195, :240-269)
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pcg_hash(uint32_t v) {
+    uint32_t s = v * 747796405u + 2891336453u;
+    uint32_t w = ((s >> ((s >> 28u) + 4u)) ^ s) * 277803737u;
+    return (w >> 22u) ^ w;
+}
+__device__ __forceinline__ float u01(uint32_t h) { return (float)(h >> 8) * (1.0f / 16777216.0f); }
+
+struct GridUpd {
+    int cascades, grid_size, warmup;
+    uint32_t g3, M;
+    float scale;
+    uint32_t seed;
+};
+
+// flag[c*g3 + i] = density_grid > thr  (input of the stream compaction that lists occupied cells)
+__global__ void k_grid_flags(const float* __restrict__ grid, int64_t n, float thr, uint8_t* __restrict__ flags) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = grid[i] > thr ? 1 : 0;
+}
+
+// Pick the cells to refresh and a jittered point inside each. Slot layout per cascade:
+//   warmup : g3 slots, slot i = Morton index i
+//   else   : 2*M slots, [0,M) uniform random cells, [M,2M) random occupied cells (skipped if none)
+__global__ void k_grid_pick(const GridUpd u, int c, const int* __restrict__ occ_list, const int* __restrict__ occ_count,
+                            int* __restrict__ cell_idx, float* __restrict__ xyz) {
+    const uint32_t n_slots = u.warmup ? u.g3 : 2u * u.M;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    uint32_t h = pcg_hash(u.seed ^ pcg_hash(i + 0x9e3779b9u * (uint32_t)(c + 1)));
+    int idx;
+    if (u.warmup) {
+        idx = (int)i;
+    } else if (i < u.M) {
+        // uniform cell: three independent coordinates, then Morton order (reference networks.py:182-184)
+        const uint32_t G = (uint32_t)u.grid_size;
+        const uint32_t cx = pcg_hash(h) % G, cy = pcg_hash(h ^ 0x68bc21ebu) % G, cz = pcg_hash(h ^ 0x02e5be93u) % G;
+        idx = (int)morton_encode3(cx, cy, cz);
+    } else {
+        const int cnt = *occ_count;
+        if (cnt <= 0) {
+            cell_idx[i] = -1;
+            xyz[3 * i] = 0.f; xyz[3 * i + 1] = 0.f; xyz[3 * i + 2] = 0.f;
+            return;
+        }
+        idx = occ_list[pcg_hash(h ^ 0x7feb352du) % (uint32_t)cnt];
+    }
+    cell_idx[i] = idx;
+    const uint32_t m = (uint32_t)idx;
+    const float G1 = (float)(u.grid_size - 1);
+    const float s = fminf(scalbnf(1.0f, c - 1), u.scale);
+    const float half_cell = s / (float)u.grid_size;
+    const uint32_t cc[3] = {morton_compact10(m), morton_compact10(m >> 1), morton_compact10(m >> 2)};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        h = pcg_hash(h + 0x85ebca6bu);
+        const float centre = ((float)cc[k] / G1 * 2.0f - 1.0f) * (s - half_cell);
+        xyz[3 * i + k] = centre + (u01(h) * 2.0f - 1.0f) * half_cell;
+    }
+}
+
+// tmp[cell] = sigma (duplicates: last writer wins, as with the reference's index_put)
+__global__ void k_grid_scatter(const int* __restrict__ cell_idx, const float* __restrict__ sigma, uint32_t n,
+                               float* __restrict__ tmp) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = cell_idx[i];
+    if (c >= 0) tmp[c] = sigma[i];
+}
+
+// grid = grid < 0 ? grid : max(grid*decay, tmp); accumulate sum / count of the positive cells
+__global__ void k_grid_merge(float* __restrict__ grid, const float* __restrict__ tmp, int64_t n, float decay,
+                             float* __restrict__ stats /* [0]=sum, [1]=count */) {
+    float s = 0.f, cnt = 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float g = grid[i];
+        if (!(g < 0.f)) g = fmaxf(g * decay, tmp[i]);
+        grid[i] = g;
+        if (g > 0.f) { s += g; cnt += 1.f; }
+    }
+    s = warp_sum(s);
+    cnt = warp_sum(cnt);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&stats[0], s);
+        atomicAdd(&stats[1], cnt);
+    }
+}
+__global__ void k_grid_mean(float* __restrict__ stats) {
+    // stats[2] = mean of the positive cells (NaN when there is none, like the reference's empty .mean())
+    stats[2] = stats[0] / stats[1];
+}
+
+// workspace layout (all 256-byte aligned):
+//   tmp (cascades*g3 f32) | flags (g3 u8) | occ_list (g3 i32) | occ_count (i32) | cell_idx (g3 i32)
+//   | xyz (g3*3 f32) | sigma (g3 f32) | stats (4 f32) | cub temp
+static size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
+static size_t select_temp_bytes(int g3) {
+    size_t bytes = 0;
+    cub::DeviceSelect::Flagged(nullptr, bytes, cub::CountingInputIterator<int>(0), (const uint8_t*)nullptr, (int*)nullptr,
+                               (int*)nullptr, g3);
+    return al256(bytes);
+}
+extern "C" size_t ngp_update_grid_workspace(int cascades, int grid_size) {
+    if (cascades < 1 || grid_size < 1) return 0;
+    const size_t g3 = (size_t)grid_size * grid_size * grid_size;
+    return al256(cascades * g3 * 4) + al256(g3) + al256(g3 * 4) + 256 + al256(g3 * 4) + al256(g3 * 12) + al256(g3 * 4) + 256 +
+           select_temp_bytes((int)g3);
+}
+
+extern "C" int ngp_update_density_grid(const NgpNet* net, float* density_grid, uint8_t* density_bitfield, int cascades,
+                                       int grid_size, float scale, float density_threshold, int warmup, float decay,
+                                       uint32_t seed, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!net || !density_grid || !density_bitfield || !workspace || cascades < 1 || grid_size < 2 || grid_size > 1024)
+        return NGP_EINVAL;
+    if (workspace_bytes < ngp_update_grid_workspace(cascades, grid_size)) return NGP_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t g3 = (size_t)grid_size * grid_size * grid_size;
+    char* w = (char*)workspace;
+    float* tmp = (float*)w; w += al256(cascades * g3 * 4);
+    uint8_t* flags = (uint8_t*)w; w += al256(g3);
+    int* occ_list = (int*)w; w += al256(g3 * 4);
+    int* occ_count = (int*)w; w += 256;
+    int* cell_idx = (int*)w; w += al256(g3 * 4);
+    float* xyz = (float*)w; w += al256(g3 * 12);
+    float* sigma = (float*)w; w += al256(g3 * 4);
+    float* stats = (float*)w; w += 256;
+    void* cub_temp = w;
+    size_t cub_bytes = select_temp_bytes((int)g3);
+
+    GridUpd u;
+    u.cascades = cascades; u.grid_size = grid_size; u.warmup = warmup ? 1 : 0;
+    u.g3 = (uint32_t)g3; u.M = (uint32_t)(g3 / 4); u.scale = scale; u.seed = seed;
+    NGP_CUDA(cudaMemsetAsync(tmp, 0, cascades * g3 * 4, st));
+    NGP_CUDA(cudaMemsetAsync(stats, 0, 16, st));
+    const uint32_t n_slots = warmup ? (uint32_t)g3 : 2u * u.M;
+    for (int c = 0; c < cascades; ++c) {
+        if (!warmup) {
+            k_grid_flags<<<ngp_div_up(g3, 256), 256, 0, st>>>(density_grid + c * g3, (int64_t)g3, density_threshold, flags);
+            NGP_CHECK_LAUNCH();
+            NGP_CUDA(cub::DeviceSelect::Flagged(cub_temp, cub_bytes, cub::CountingInputIterator<int>(0), flags, occ_list,
+                                                occ_count, (int)g3, st));
+        }
+        k_grid_pick<<<ngp_div_up(n_slots, 256), 256, 0, st>>>(u, c, occ_list, occ_count, cell_idx, xyz);
+        NGP_CHECK_LAUNCH();
+        NgpSamples smp;
+        smp.xyzs = xyz; smp.dirs = nullptr; smp.rays_o = nullptr; smp.rays_d = nullptr; smp.ray_idx = nullptr; smp.ts = nullptr;
+        smp.n = n_slots; smp.n_dev = nullptr;
+        int rc = ngp_net_forward(net, &smp, 0, sigma, nullptr, nullptr, nullptr, stream);
+        if (rc) return rc;
+        k_grid_scatter<<<ngp_div_up(n_slots, 256), 256, 0, st>>>(cell_idx, sigma, n_slots, tmp + c * g3);
+        NGP_CHECK_LAUNCH();
+    }
+    int grid = ngp_div_up((int64_t)cascades * g3, 256);
+    if (grid > ngp_sm_count() * 8) grid = ngp_sm_count() * 8;
+    k_grid_merge<<<grid, 256, 0, st>>>(density_grid, tmp, (int64_t)cascades * g3, decay, stats);
+    NGP_CHECK_LAUNCH();
+    k_grid_mean<<<1, 1, 0, st>>>(stats);
+    NGP_CHECK_LAUNCH();
+    // threshold = min(mean, density_threshold) evaluated on the device (fminf ignores a NaN mean)
+    return ngp_packbits(density_grid, 0, (int64_t)cascades * g3 / 8, density_threshold, stats + 2, density_bitfield, stream);
+}

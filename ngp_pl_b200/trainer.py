@@ -1,0 +1,259 @@
+"""Sync-free training step on the fused C-ABI path (what reference train.py:159-185 does per step, plus
+the optimiser PL runs after it and the every-16-steps occupancy refresh of train.py:160-163):
+
+    [device RNG -> batch assembly] -> ngp_render_train_fwd -> ngp_nerf_loss_grad -> ngp_render_train_bwd
+    -> [one NCCL all-reduce of the flat gradient buffer] -> ngp_adam_step (+fp16 re-cast, +grad zero)
+
+All of it is stream-ordered launches with no host synchronisation, so `capture()` records it into one
+CUDA graph. Parameters live in ONE flat fp32 buffer [xyz_encoder.params | rgb_net.params] (the
+nn.Parameters of the NGP module are views into it, so state_dict()/checkpoints keep the reference's
+keys and layouts); gradients, Adam moments and the fp16 working copy mirror that layout.
+
+Data parallelism (reference train.py:269-272: DDP, one process per GPU, every rank draws its own
+batch => weak scaling): a single `all_reduce(SUM)` over the flat gradient buffer per step, averaged
+inside the Adam kernel (grad_mul = 1/world_size). The occupancy bitfield is refreshed by every rank
+from identical parameters and then broadcast from rank 0 so all ranks march the same grid.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from .models.networks import NGP, feat_save_bytes
+from .models.rendering import MAX_SAMPLES, NEAR_DISTANCE
+
+
+class Trainer:
+    def __init__(self, model: NGP, n_rays=8192, lr=1e-2, exp_step_factor=0.0, bg=(1.0, 1.0, 1.0), lambda_opacity=1e-3,
+                 T_threshold=1e-4, betas=(0.9, 0.999), eps=1e-15, max_total_samples=None, update_interval=16,
+                 warmup_steps=256, process_group=None, world_size=1, rank=0, seed=0, materialize_ws=False):
+        self.model = model
+        dev = model.density_bitfield.device
+        if dev.type != "cuda":
+            raise RuntimeError("ngp_pl_b200.Trainer needs the model on a CUDA device (there is no CPU path)")
+        self.dev = dev
+        self.n_rays = int(n_rays)
+        self.lr = float(lr)
+        self.betas, self.eps = betas, float(eps)
+        self.update_interval, self.warmup_steps = update_interval, warmup_steps
+        self.pg, self.world_size, self.rank = process_group, int(world_size), int(rank)
+        self.exp_step_factor = float(exp_step_factor)
+        self.host_step = 0
+        self.seed = seed
+        L = _lib.lib()
+
+        # ---- flat parameter / gradient / optimiser state --------------------------------------------------
+        pe, pr = model.xyz_encoder.params, model.rgb_net.params
+        self.n_enc, self.n_rgb = pe.numel(), pr.numel()
+        n = self.n_enc + self.n_rgb
+        self.n_params = n
+        with torch.cuda.device(dev):
+            self.P = torch.empty(n, device=dev, dtype=torch.float32)
+            self.P[:self.n_enc].copy_(pe.data)
+            self.P[self.n_enc:].copy_(pr.data)
+            pe.data = self.P[:self.n_enc]
+            pr.data = self.P[self.n_enc:]
+            self.G = torch.zeros(n, device=dev, dtype=torch.float32)
+            self.M = torch.zeros(n, device=dev, dtype=torch.float32)
+            self.V = torch.zeros(n, device=dev, dtype=torch.float32)
+            self.Ph = torch.empty(n, device=dev, dtype=torch.float16)
+            _lib.check(L.ngp_cast_params(self.P.data_ptr(), self.Ph.data_ptr(), n, self._st()), "cast_params")
+            self.lr_dev = torch.full((1,), self.lr, device=dev, dtype=torch.float32)
+            self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+
+            # ---- network descriptor pointing at the flat fp16 copy -----------------------------------------
+            net = _lib.NgpNet()
+            net.enc_params_h = self.Ph.data_ptr()
+            net.rgb_params_h = self.Ph[self.n_enc:].data_ptr()
+            net.meta = model.xyz_encoder.meta
+            for k in range(3):
+                net.xyz_min[k] = model._xyz_min_host[k]
+                net.xyz_max[k] = model._xyz_max_host[k]
+            net.rgb_act = model.rgb_net.rgb_act
+            self.net = net
+
+            # ---- step configuration -------------------------------------------------------------------------
+            cfg = _lib.NgpTrainCfg()
+            cfg.n_rays = self.n_rays
+            cfg.cascades = model.cascades
+            cfg.grid_size = model.grid_size
+            cfg.max_samples = MAX_SAMPLES
+            cfg.scale = float(model.scale)
+            cfg.exp_step_factor = self.exp_step_factor
+            cfg.T_threshold = float(T_threshold)
+            cfg.near_distance = NEAR_DISTANCE
+            c, h = model.center.flatten().tolist(), model.half_size.flatten().tolist()
+            for k in range(3):
+                cfg.center[k], cfg.half_size[k], cfg.bg[k] = c[k], h[k], float(bg[k])
+            cfg.lambda_opacity = float(lambda_opacity)
+            cap = int(max_total_samples) if max_total_samples else self.n_rays * MAX_SAMPLES
+            cfg.max_total_samples = cap
+            self.cfg = cfg
+            self.capacity = cap
+
+            # ---- buffers ------------------------------------------------------------------------------------
+            f32 = dict(device=dev, dtype=torch.float32)
+            i32 = dict(device=dev, dtype=torch.int32)
+            N = self.n_rays
+            self.rays_o = torch.zeros(N, 3, **f32)
+            self.rays_d = torch.zeros(N, 3, **f32)
+            self.rgb_gt = torch.zeros(N, 3, **f32)
+            self.noise = torch.zeros(N, **f32)
+            self.stage_t = torch.empty(N * MAX_SAMPLES, **f32)
+            self.stage_dt = torch.empty(N * MAX_SAMPLES, **f32)
+            self.n_samples = torch.zeros(N, **i32)
+            self.offsets = torch.zeros(N, **i32)
+            self.counters = torch.zeros(4, **i32)
+            self.rgb = torch.zeros(N, 3, **f32)
+            self.opacity = torch.zeros(N, **f32)
+            self.depth = torch.zeros(N, **f32)
+            self.ray_idx = torch.empty(cap, **i32)
+            self.ts = torch.empty(cap, **f32)
+            self.deltas = torch.empty(cap, **f32)
+            self.sigmas = torch.empty(cap, **f32)
+            self.rgbs = torch.empty(cap, 3, **f32)
+            self.ws = torch.empty(cap, **f32) if materialize_ws else None
+            self.dsigmas = torch.empty(cap, **f32)
+            self.drgbs = torch.empty(cap, 3, **f32)
+            self.feat_save = torch.empty(feat_save_bytes(cap), device=dev, dtype=torch.uint8)
+            self.scalars = torch.zeros(8, **f32)
+            self.dL_drgb = torch.zeros(N, 3, **f32)
+            self.dL_dopacity = torch.zeros(N, **f32)
+            scan_bytes = L.ngp_train_scan_temp_bytes(N)
+            self.scan_temp = torch.empty(scan_bytes, device=dev, dtype=torch.uint8)
+            b = _lib.NgpTrainBuffers()
+            for name in ("rays_o", "rays_d", "noise", "stage_t", "stage_dt", "n_samples", "offsets", "counters", "rgb",
+                         "opacity", "depth", "ray_idx", "ts", "deltas", "sigmas", "rgbs", "dsigmas", "drgbs", "feat_save",
+                         "scalars", "scan_temp"):
+                setattr(b, name, getattr(self, name).data_ptr())
+            b.ws = self.ws.data_ptr() if self.ws is not None else None
+            b.density_bitfield = model.density_bitfield.data_ptr()
+            b.scan_temp_bytes = scan_bytes
+            self.buf = b
+
+            # ---- occupancy grid ----------------------------------------------------------------------------
+            G3 = model.grid_size ** 3
+            if not hasattr(model, "density_grid"):
+                model.register_buffer("density_grid", torch.zeros(model.cascades, G3, **f32))
+            ws_bytes = L.ngp_update_grid_workspace(model.cascades, model.grid_size)
+            self.grid_ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+            self.gen = torch.Generator(device=dev)
+            self.gen.manual_seed(seed + 1000 * self.rank)
+        self.graph = None
+        self.bank = None
+
+    # ------------------------------------------------------------------------------------------------------
+    def _st(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def set_lr(self, lr):
+        self.lr_dev.fill_(float(lr))
+
+    def update_density_grid(self, density_threshold=0.01 * MAX_SAMPLES / 3 ** 0.5, warmup=False, decay=0.95):
+        """device-side equivalent of NGP.update_density_grid (reference networks.py:240-269); no host sync"""
+        m = self.model
+        with torch.cuda.device(self.dev):
+            rc = _lib.lib().ngp_update_density_grid(
+                C.byref(self.net), m.density_grid.data_ptr(), m.density_bitfield.data_ptr(), m.cascades, m.grid_size,
+                float(m.scale), float(density_threshold), int(bool(warmup)), float(decay),
+                (self.seed * 2654435761 + self.host_step * 40503 + 12345) & 0xffffffff,
+                self.grid_ws.data_ptr(), self.grid_ws.numel(), self._st())
+            _lib.check(rc, "update_density_grid")
+            if self.world_size > 1:
+                import torch.distributed as dist
+                dist.broadcast(m.density_bitfield, src=0, group=self.pg)
+
+    # ---- pieces of one step (all asynchronous) -------------------------------------------------------------
+    def attach_bank(self, bank):
+        """bank: synth.RayBank (directions, poses, uint8 images on the device)"""
+        self.bank = bank
+        self.img_idx = torch.zeros(self.n_rays, device=self.dev, dtype=torch.int64)
+        self.pix_idx = torch.zeros(self.n_rays, device=self.dev, dtype=torch.int64)
+
+    def sample_batch(self):
+        """random (image, pixel) pairs with replacement (reference datasets/base.py:22-30) + ray assembly"""
+        bk = self.bank
+        self.img_idx.random_(0, bk.poses.shape[0], generator=self.gen)
+        self.pix_idx.random_(0, bk.directions.shape[0], generator=self.gen)
+        rc = _lib.lib().ngp_gen_rays(self.img_idx.data_ptr(), self.pix_idx.data_ptr(), bk.poses.data_ptr(),
+                                     bk.directions.data_ptr(), bk.rgb.data_ptr(), bk.directions.shape[0], self.n_rays,
+                                     self.rays_o.data_ptr(), self.rays_d.data_ptr(), self.rgb_gt.data_ptr(), self._st())
+        _lib.check(rc, "gen_rays")
+
+    def set_batch(self, rays_o, rays_d, rgb_gt):
+        self.rays_o.copy_(rays_o, non_blocking=True)
+        self.rays_d.copy_(rays_d, non_blocking=True)
+        self.rgb_gt.copy_(rgb_gt, non_blocking=True)
+
+    def forward(self):
+        self.noise.uniform_(0, 1, generator=self.gen)
+        _lib.check(_lib.lib().ngp_render_train_fwd(C.byref(self.net), C.byref(self.cfg), C.byref(self.buf), self._st()),
+                   "render_train_fwd")
+
+    def loss_backward(self):
+        L = _lib.lib()
+        self.scalars[2:4].zero_()
+        _lib.check(L.ngp_nerf_loss_grad(C.byref(self.cfg), C.byref(self.buf), self.rgb_gt.data_ptr(),
+                                        self.dL_drgb.data_ptr(), self.dL_dopacity.data_ptr(), self._st()), "nerf_loss_grad")
+        _lib.check(L.ngp_render_train_bwd(C.byref(self.net), C.byref(self.cfg), C.byref(self.buf), self.dL_drgb.data_ptr(),
+                                          self.dL_dopacity.data_ptr(), None, None, self.G.data_ptr(),
+                                          self.G[self.n_enc:].data_ptr(), self._st()), "render_train_bwd")
+
+    def allreduce(self):
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.G, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def optimizer_step(self):
+        rc = _lib.lib().ngp_adam_step(self.P.data_ptr(), self.G.data_ptr(), self.M.data_ptr(), self.V.data_ptr(),
+                                      self.Ph.data_ptr(), self.n_params, self.lr_dev.data_ptr(), self.step_dev.data_ptr(),
+                                      self.betas[0], self.betas[1], self.eps, 1.0 / self.world_size, 1, self._st())
+        _lib.check(rc, "adam_step")
+
+    def _step_body(self, sample):
+        if sample:
+            self.sample_batch()
+        self.forward()
+        self.loss_backward()
+        self.allreduce()
+        self.optimizer_step()
+
+    def capture(self, sample=True):
+        """record one optimiser step into a CUDA graph (warm up on a side stream first)"""
+        s = torch.cuda.Stream(self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            # one eager run so lazy initialisation (cudaFuncSetAttribute, NCCL communicators) is done
+            saved = [t.clone() for t in (self.P, self.M, self.V, self.Ph, self.G, self.step_dev)]
+            self._step_body(sample)
+            for t, v in zip((self.P, self.M, self.V, self.Ph, self.G, self.step_dev), saved):
+                t.copy_(v)
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        self.gen_states = None
+        g.register_generator_state(self.gen)
+        with torch.cuda.graph(g):
+            self._step_body(sample)
+        self.graph = g
+        self._graph_samples = sample
+
+    def train_step(self, sample=True):
+        """one full training step incl. the occupancy refresh cadence of reference train.py:160-163"""
+        if self.host_step % self.update_interval == 0:
+            self.update_density_grid(warmup=self.host_step < self.warmup_steps)
+        if self.graph is not None and self._graph_samples == sample:
+            self.graph.replay()
+        else:
+            self._step_body(sample)
+        self.host_step += 1
+
+    # ---- read-backs (these DO synchronise; not used inside the timed loop) -----------------------------------
+    def stats(self):
+        c = self.counters.tolist()
+        s = self.scalars.tolist()
+        n = self.n_rays
+        mse = s[2] / (3 * n)
+        return dict(rm_samples=c[0], vr_samples=c[1], mse=mse, psnr=-10 * math.log10(max(mse, 1e-12)),
+                    loss=mse + self.cfg.lambda_opacity * s[3] / n)

@@ -208,8 +208,9 @@ def ngp_forward_c(meta, enc_params, rgb_params, xyz_min, xyz_max, xyzs, dirs, wa
 # torch-CPU restatement of the tinycudann modules (gradient oracle)
 # ---------------------------------------------------------------------------------------------------
 def _rt(x):
-    """fp16 rounding point with a straight-through gradient"""
-    return x.half().float()
+    """fp16 rounding point with a straight-through fp32 gradient (x.half().float() alone would also
+    round the GRADIENT to fp16 and flush small gradients to zero)"""
+    return x + (x.half().float() - x).detach()
 
 
 def torch_grid_encode(meta, table, x01):

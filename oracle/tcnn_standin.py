@@ -21,7 +21,8 @@ class _Meta:
 
 
 def _rt(x):
-    return x.half().float()
+    # fp16 rounding of the value, fp32 straight-through gradient
+    return x + (x.half().float() - x).detach()
 
 
 class NetworkWithInputEncoding(nn.Module):
