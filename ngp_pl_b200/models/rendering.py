@@ -6,10 +6,12 @@ output_radiance (`exposure` belongs to the HDR tonemapper path, outside the hot 
 Result keys -- train: deltas, ts, rm_samples, vr_samples, opacity, depth, rgb, ws, rays_a;
 test: opacity, depth, rgb, total_samples.
 """
+import ctypes as C
+
 import torch
 
 from .custom_functions import RayAABBIntersector, RayMarcher, VolumeRenderer
-from .. import vren
+from .. import _lib, vren
 
 MAX_SAMPLES = 1024
 NEAR_DISTANCE = 0.01
@@ -25,7 +27,12 @@ def render(model, rays_o, rays_d, **kwargs):
     t0 = hits_t[:, 0, 0]
     hits_t[:, 0, 0] = torch.where((t0 >= 0) & (t0 < NEAR_DISTANCE), torch.full_like(t0, NEAR_DISTANCE), t0)
 
-    fn = _render_rays_test if kwargs.get('test_time', False) else _render_rays_train
+    if kwargs.get('test_time', False):
+        # default: the sync-free device-side wavefront (ngp_render_infer); fused=False runs the
+        # reference-shaped host loop over the unfused operators (kept for operator-level parity)
+        fn = _render_rays_test_fused if kwargs.get('fused', True) else _render_rays_test
+    else:
+        fn = _render_rays_train
     results = fn(model, rays_o, rays_d, hits_t, **kwargs)
     if kwargs.get('to_cpu', False):
         for k, v in results.items():
@@ -43,6 +50,44 @@ def _background(exp_step_factor, device, random_bg=False):
     if random_bg:
         return torch.rand(3, device=device)
     return torch.zeros(3, device=device)
+
+
+@torch.no_grad()
+def _render_rays_test_fused(model, rays_o, rays_d, hits_t, **kwargs):
+    """Inference through ngp_render_infer: no host synchronisation, one call per image."""
+    from .networks import _net_struct
+    exp_step_factor = kwargs.get('exp_step_factor', 0.)
+    N = rays_o.shape[0]
+    dev = rays_o.device
+    rays_o = rays_o.float().contiguous()
+    rays_d = rays_d.float().contiguous()
+    with torch.cuda.device(dev):
+        L = _lib.lib()
+        cfg = _lib.NgpInferCfg()
+        cfg.n_rays, cfg.cascades, cfg.grid_size, cfg.max_samples = N, model.cascades, model.grid_size, MAX_SAMPLES
+        cfg.scale, cfg.exp_step_factor = float(model.scale), float(exp_step_factor)
+        cfg.T_threshold, cfg.near_distance = float(kwargs.get('T_threshold', 1e-4)), NEAR_DISTANCE
+        c, h = model.center.flatten().tolist(), model.half_size.flatten().tolist()
+        bg = 1.0 if exp_step_factor == 0 else 0.0
+        for k in range(3):
+            cfg.center[k], cfg.half_size[k], cfg.bg[k] = c[k], h[k], bg
+        cfg.sample_budget = int(kwargs.get('max_samples', MAX_SAMPLES))
+        cfg.max_round_samples = max(4 * N, 1 << 16)
+        ws_bytes = L.ngp_render_infer_workspace(N, cfg.max_round_samples)
+        cache = getattr(model, '_infer_ws', None)
+        if cache is None or cache.numel() < ws_bytes or cache.device != dev:
+            cache = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+            model._infer_ws = cache
+        net, keep = _net_struct(model)
+        opacity = torch.empty(N, device=dev)
+        depth = torch.empty(N, device=dev)
+        rgb = torch.empty(N, 3, device=dev)
+        total = torch.zeros(1, device=dev, dtype=torch.int64)
+        rc = L.ngp_render_infer(C.byref(net), C.byref(cfg), rays_o.data_ptr(), rays_d.data_ptr(),
+                                model.density_bitfield.data_ptr(), opacity.data_ptr(), depth.data_ptr(), rgb.data_ptr(),
+                                total.data_ptr(), cache.data_ptr(), cache.numel(), torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "render_infer")
+    return {'opacity': opacity, 'depth': depth, 'rgb': rgb, 'total_samples': total[0]}
 
 
 @torch.no_grad()

@@ -47,6 +47,16 @@ class _HalfCopy:
         return self.buf
 
 
+class _FixedHalf:
+    """fp16 working copy owned by someone else (the Trainer's flat buffer, refreshed by its Adam kernel)"""
+
+    def __init__(self, buf):
+        self.buf = buf
+
+    def get(self, p):
+        return self.buf
+
+
 class Encoding(nn.Module):
     """tcnn.Encoding(n_input_dims=3, {"otype": "SphericalHarmonics", "degree": 4}); reference networks.py:58-65.
     Parameter-free (empty `params`, as in tinycudann)."""

@@ -59,6 +59,10 @@ class Trainer:
             self.V = torch.zeros(n, device=dev, dtype=torch.float32)
             self.Ph = torch.empty(n, device=dev, dtype=torch.float16)
             _lib.check(L.ngp_cast_params(self.P.data_ptr(), self.Ph.data_ptr(), n, self._st()), "cast_params")
+            # the module-level API (NGP.forward / density / render) must see the weights this trainer updates
+            from .tcnn import _FixedHalf
+            model.xyz_encoder._half = _FixedHalf(self.Ph[:self.n_enc])
+            model.rgb_net._half = _FixedHalf(self.Ph[self.n_enc:])
             self.lr_dev = torch.full((1,), self.lr, device=dev, dtype=torch.float32)
             self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
 
