@@ -127,7 +127,7 @@ def peaks():
 
 
 # --------------------------------------------------------------------------------------------------
-def cpu_baseline_port(n_rays=1024):
+def cpu_baseline_port(n_rays=16384):
     """The C oracle (a port: the reference has no CPU path) rendering a bounded sample of the same
     workload on one host core: march + network forward + compositing. Forward only -- the C oracle has no
     backward -- so this is an UPPER bound on what a CPU training step could reach."""
@@ -398,11 +398,14 @@ def run_reference(args):
     state = {"step": 0, "res": None}
 
     def step():
-        if state["step"] % 16 == 0:
-            model.update_density_grid(0.01 * 1024 / 3 ** 0.5, warmup=state["step"] < 256)
-        o, d, rgb = bank.sample(N_RAYS)
-        res = ref.render(model, o, d)
-        loss = sum(v.mean() for v in loss_fn(res, {"rgb": rgb}).values())
+        # PL runs training_step under fp16 autocast (Trainer(precision=16), train.py:274); the stand-in
+        # computes with fp32 gradients, so no GradScaler is needed (which only favours this arm)
+        with torch.autocast("cuda", dtype=torch.float16):
+            if state["step"] % 16 == 0:
+                model.update_density_grid(0.01 * 1024 / 3 ** 0.5, warmup=state["step"] < 256)
+            o, d, rgb = bank.sample(N_RAYS)
+            res = ref.render(model, o, d)
+            loss = sum(v.mean() for v in loss_fn(res, {"rgb": rgb}).values())
         opt.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()

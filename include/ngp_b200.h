@@ -260,12 +260,18 @@ typedef struct {
     float scale, exp_step_factor, T_threshold, near_distance;
     float center[3], half_size[3], bg[3];
     int32_t sample_budget;      /* reference kwarg `max_samples` of the outer loop (default 1024) */
-    int64_t max_round_samples;  /* capacity of the per-round sample buffers (rays that do not fit wait a round) */
+    int64_t max_round_samples;  /* capacity of the per-round sample buffers, shared fairly by the alive rays */
 } NgpInferCfg;
 
 size_t ngp_render_infer_workspace(int n_rays, int64_t max_round_samples);
+/* Runs rounds [first_round, first_round+n_rounds) of the wavefront (first_round == 0 initialises; finish != 0
+ * adds the background and writes total_samples). Per round every alive ray takes up to
+ * min(2,2,4,4,...,64 schedule, max_round_samples / n_alive) samples. alive_count_out (device int32*, optional)
+ * gets the number of rays still alive afterwards -- reading it back every few rounds is the only host
+ * synchronisation of the path. Requires max_round_samples >= n_rays. */
 int ngp_render_infer(const NgpNet* net, const NgpInferCfg* cfg, const float* rays_o, const float* rays_d,
                      const uint8_t* density_bitfield, float* opacity, float* depth, float* rgb, int64_t* total_samples,
+                     int first_round, int n_rounds, int finish, int* alive_count_out,
                      void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus

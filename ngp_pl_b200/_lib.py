@@ -133,7 +133,8 @@ SIGNATURES = {
     "ngp_adam_step": (_i, [_P, _P, _P, _P, _P, _i64, _P, _P, _f, _f, _f, _f, _i, _P]),
     "ngp_gen_rays": (_i, [_P, _P, _P, _P, _P, _i64, _i, _P, _P, _P, _P]),
     "ngp_render_infer_workspace": (_sz, [_i, _i64]),
-    "ngp_render_infer": (_i, [C.POINTER(NgpNet), C.POINTER(NgpInferCfg), _P, _P, _P, _P, _P, _P, _P, _P, _sz, _P]),
+    "ngp_render_infer": (_i, [C.POINTER(NgpNet), C.POINTER(NgpInferCfg), _P, _P, _P, _P, _P, _P, _P, _i, _i, _i, _P,
+                              _P, _sz, _P]),
     "ngp_update_grid_workspace": (_sz, [_i, _i]),
     "ngp_update_density_grid": (_i, [C.POINTER(NgpNet), _P, _P, _i, _i, _f, _f, _i, _f, C.c_uint32, _P, _sz, _P]),
 }

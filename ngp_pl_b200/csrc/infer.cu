@@ -13,7 +13,6 @@
 #include "march.cuh"
 #include "../../include/ngp_b200.h"
 
-#define INFER_MAX_ROUNDS 64
 
 // init: AABB (+ near clamp), zero the accumulators, build the first alive list
 __global__ void k_infer_init(const NgpInferCfg cfg, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
@@ -52,20 +51,46 @@ __global__ void k_infer_init(const NgpInferCfg cfg, const float* __restrict__ ra
     }
 }
 
+// per-round bookkeeping (1 thread): fair share of the sample buffers, budget accounting, counter reset.
+//   S_eff = clamp(capacity / n_alive, 1, S_sched)   (the reference's N_samples = min(N_rays // N_alive, 64) idea,
+//   rendering.py:80, so n_alive * S_eff always fits);  once the requested total reaches the reference's
+//   loop budget (`max_samples` kwarg, rendering.py:75) the remaining rays are dropped, as its loop exit does.
+// state: [0] S_eff  [1] requested so far  [2] sample count of this round  [3] rounds run
+__global__ void k_infer_round_begin(const NgpInferCfg cfg, const int S_sched, int* __restrict__ alive_count,
+                                    int* __restrict__ next_count, int* __restrict__ state, int64_t* __restrict__ total) {
+    *total += state[2];
+    state[2] = 0;
+    *next_count = 0;
+    int n_alive = *alive_count;
+    if (state[1] >= cfg.sample_budget) {
+        n_alive = 0;
+        *alive_count = 0;
+    }
+    int S = S_sched;
+    if (n_alive > 0) {
+        const int64_t share = cfg.max_round_samples / n_alive;
+        if (share < S) S = (int)(share < 1 ? 1 : share);
+        state[1] += S;
+        state[3] += 1;
+    }
+    state[0] = S;
+}
+
 // one round of marching: every alive ray takes up to S occupied samples (staged in shared memory),
 // then the warp claims a contiguous range of the compact sample arrays with one atomic.
-__global__ void k_infer_march(const NgpInferCfg cfg, const int S, const float* __restrict__ rays_o,
+__global__ void k_infer_march(const NgpInferCfg cfg, const int S_max, const float* __restrict__ rays_o,
                               const float* __restrict__ rays_d, const uint8_t* __restrict__ bitfield,
                               float* __restrict__ t_cur, const float* __restrict__ t_end, const int* __restrict__ alive,
                               const int* __restrict__ alive_count, int* __restrict__ ray_start, int* __restrict__ ray_n,
                               int* __restrict__ ray_idx, float* __restrict__ ts, float* __restrict__ deltas,
-                              int* __restrict__ sample_count) {
-    extern __shared__ float2 stage[];  // [blockDim.x][S]
+                              int* __restrict__ state) {
+    extern __shared__ float2 stage[];  // [blockDim.x][S_max]
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int n_alive = *alive_count;
     if ((int)(blockIdx.x * blockDim.x) >= n_alive) return;
-    float2* my = stage + (size_t)threadIdx.x * S;
+    const int S = min(state[0], S_max);
+    float2* my = stage + (size_t)threadIdx.x * S_max;
     int n = 0, r = -1;
     float t = 0.f;
     if (i < n_alive) {
@@ -94,15 +119,10 @@ __global__ void k_infer_march(const NgpInferCfg cfg, const int S, const float* _
     }
     const int warp_total = __shfl_sync(0xffffffffu, pre, 31);
     int base = 0;
-    if (lane == 31 && warp_total > 0) base = atomicAdd(sample_count, warp_total);
+    if (lane == 31 && warp_total > 0) base = atomicAdd(&state[2], warp_total);
     base = __shfl_sync(0xffffffffu, base, 31);
     if (r < 0) return;
-    int start = base + pre - n;
-    // capacity clamp: a ray that does not fit keeps its samples for the next round (t_cur not advanced)
-    if ((int64_t)start + n > cfg.max_round_samples) {
-        n = (int)max((int64_t)0, cfg.max_round_samples - start);
-        t = n > 0 ? __fadd_rn(my[n - 1].x, my[n - 1].y) : t_cur[r];
-    }
+    const int start = base + pre - n;  // n_alive * S <= capacity, so this always fits
     ray_start[i] = start;
     ray_n[i] = n;
     t_cur[r] = t;
@@ -113,17 +133,9 @@ __global__ void k_infer_march(const NgpInferCfg cfg, const int S, const float* _
     }
 }
 
-// clamp the claimed sample count to the capacity (the network kernel reads it as its `n`)
-__global__ void k_infer_clamp(int* __restrict__ sample_count, int64_t cap, int64_t* __restrict__ total) {
-    int v = *sample_count;
-    if (v > cap) v = (int)cap;
-    *sample_count = v;
-    *total += v;
-}
-
 // composite this round's samples of every alive ray (one thread per ray, <= 64 samples, same serial
 // order as the reference's composite_test_fw_kernel) and append the survivors to the next alive list
-__global__ void k_infer_composite(const NgpInferCfg cfg, const int S, const float* __restrict__ sigmas,
+__global__ void k_infer_composite(const NgpInferCfg cfg, const float* __restrict__ sigmas,
                                   const float* __restrict__ rgbs, const float* __restrict__ deltas,
                                   const float* __restrict__ ts, const int* __restrict__ ray_start,
                                   const int* __restrict__ ray_n, const float* __restrict__ t_cur,
@@ -176,8 +188,10 @@ __global__ void k_infer_composite(const NgpInferCfg cfg, const int S, const floa
     }
 }
 
-__global__ void k_infer_finish(const NgpInferCfg cfg, const float* __restrict__ opacity, float* __restrict__ rgb) {
+__global__ void k_infer_finish(const NgpInferCfg cfg, const float* __restrict__ opacity, float* __restrict__ rgb,
+                               const int* __restrict__ state, int64_t* __restrict__ total, int64_t* __restrict__ total_out) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r == 0 && total_out) *total_out = *total + state[2];
     if (r >= cfg.n_rays) return;
     const float rest = 1.0f - opacity[r];  // reference rendering.py:112-116
     rgb[3 * r] += cfg.bg[0] * rest;
@@ -199,12 +213,19 @@ extern "C" size_t ngp_render_infer_workspace(int n_rays, int64_t max_round_sampl
     return 6 * nr + 7 * ns + 4096;
 }
 
+// Runs rounds [first_round, first_round + n_rounds) of the wavefront. first_round == 0 also initialises
+// (AABB, accumulators, first alive list); finish != 0 adds the background and writes total_samples.
+// alive_count_out (device int32*, optional) receives the number of rays still alive after the last round
+// of this call: the caller may read it back every few rounds to stop early (the ONLY host sync of the
+// path, amortised over n_rounds), or never read it and simply run enough rounds.
 extern "C" int ngp_render_infer(const NgpNet* net, const NgpInferCfg* cfg, const float* rays_o, const float* rays_d,
                                 const uint8_t* density_bitfield, float* opacity, float* depth, float* rgb,
-                                int64_t* total_samples, void* workspace, size_t workspace_bytes, void* stream) {
+                                int64_t* total_samples, int first_round, int n_rounds, int finish, int* alive_count_out,
+                                void* workspace, size_t workspace_bytes, void* stream) {
     if (!net || !cfg || !rays_o || !rays_d || !density_bitfield || !opacity || !depth || !rgb || !workspace) return NGP_EINVAL;
     if (cfg->n_rays < 1 || cfg->cascades < 1 || cfg->grid_size < 1 || cfg->grid_size > 1024 || cfg->max_samples < 1 ||
-        cfg->max_round_samples < 64 || cfg->max_round_samples > 0x7fffffffll || cfg->sample_budget < 1)
+        cfg->max_round_samples < cfg->n_rays || cfg->max_round_samples > 0x7fffffffll || cfg->sample_budget < 1 ||
+        first_round < 0 || n_rounds < 0)
         return NGP_EINVAL;
     if (workspace_bytes < ngp_render_infer_workspace(cfg->n_rays, cfg->max_round_samples)) return NGP_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
@@ -224,45 +245,44 @@ extern "C" int ngp_render_infer(const NgpNet* net, const NgpInferCfg* cfg, const
     float* deltas = (float*)w; w += ns;
     float* sigmas = (float*)w; w += ns;
     float* rgbs = (float*)w; w += 3 * ns;
-    int* counters = (int*)w;  // [0..64] alive counts per round, [128..191] sample counts per round, [256..257] int64 total
+    int* counters = (int*)w;  // [0],[1] alive counts (ping-pong)  [8..11] state  [16..17] int64 total
     int* alive_cnt = counters;
-    int* sample_cnt = counters + 128;
-    int64_t* total = (int64_t*)(counters + 256);
-    NGP_CUDA(cudaMemsetAsync(counters, 0, 4096, st));
+    int* state = counters + 8;
+    int64_t* total = (int64_t*)(counters + 16);
 
-    k_infer_init<<<ngp_div_up(n, 256), 256, 0, st>>>(*cfg, rays_o, rays_d, t_cur, t_end, opacity, depth, rgb, alive[0],
-                                                      alive_cnt);
-    NGP_CHECK_LAUNCH();
-    static bool attr_set = false;
-    if (!attr_set) {
-        NGP_CUDA(cudaFuncSetAttribute(k_infer_march, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 64 * 8));
-        attr_set = true;
+    if (first_round == 0) {
+        NGP_CUDA(cudaMemsetAsync(counters, 0, 4096, st));
+        k_infer_init<<<ngp_div_up(n, 256), 256, 0, st>>>(*cfg, rays_o, rays_d, t_cur, t_end, opacity, depth, rgb, alive[0],
+                                                          alive_cnt);
+        NGP_CHECK_LAUNCH();
     }
-    int requested = 0;
-    for (int round = 0; round < INFER_MAX_ROUNDS && requested < cfg->sample_budget; ++round) {
+    for (int round = first_round; round < first_round + n_rounds; ++round) {
         const int S = round_samples(round);
-        requested += S;
+        const int cur = round & 1, nxt = cur ^ 1;
         const int bs = 64;
         // the launch covers the worst case (all rays alive); blocks past the device-side count exit at once
         const int grid = ngp_div_up(n, bs);
-        k_infer_march<<<grid, bs, (size_t)bs * S * sizeof(float2), st>>>(
-            *cfg, S, rays_o, rays_d, density_bitfield, t_cur, t_end, alive[round & 1], alive_cnt + round, ray_start, ray_n,
-            ray_idx, ts, deltas, sample_cnt + round);
+        k_infer_round_begin<<<1, 1, 0, st>>>(*cfg, S, alive_cnt + cur, alive_cnt + nxt, state, total);
         NGP_CHECK_LAUNCH();
-        k_infer_clamp<<<1, 1, 0, st>>>(sample_cnt + round, cfg->max_round_samples, total);
+        k_infer_march<<<grid, bs, (size_t)bs * S * sizeof(float2), st>>>(
+            *cfg, S, rays_o, rays_d, density_bitfield, t_cur, t_end, alive[cur], alive_cnt + cur, ray_start, ray_n,
+            ray_idx, ts, deltas, state);
         NGP_CHECK_LAUNCH();
         NgpSamples smp;
         smp.xyzs = nullptr; smp.dirs = nullptr; smp.rays_o = rays_o; smp.rays_d = rays_d; smp.ray_idx = ray_idx; smp.ts = ts;
-        smp.n = cfg->max_round_samples; smp.n_dev = sample_cnt + round;
+        smp.n = cfg->max_round_samples; smp.n_dev = state + 2;
         int rc = ngp_net_forward(net, &smp, 1, sigmas, rgbs, nullptr, nullptr, stream);
         if (rc) return rc;
-        k_infer_composite<<<grid, bs, 0, st>>>(*cfg, S, sigmas, rgbs, deltas, ts, ray_start, ray_n, t_cur, t_end,
-                                                alive[round & 1], alive_cnt + round, opacity, depth, rgb,
-                                                alive[(round + 1) & 1], alive_cnt + round + 1);
+        k_infer_composite<<<grid, bs, 0, st>>>(*cfg, sigmas, rgbs, deltas, ts, ray_start, ray_n, t_cur, t_end, alive[cur],
+                                                alive_cnt + cur, opacity, depth, rgb, alive[nxt], alive_cnt + nxt);
         NGP_CHECK_LAUNCH();
     }
-    k_infer_finish<<<ngp_div_up(n, 256), 256, 0, st>>>(*cfg, opacity, rgb);
-    NGP_CHECK_LAUNCH();
-    if (total_samples) NGP_CUDA(cudaMemcpyAsync(total_samples, total, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    if (alive_count_out)
+        NGP_CUDA(cudaMemcpyAsync(alive_count_out, alive_cnt + ((first_round + n_rounds) & 1), sizeof(int),
+                                 cudaMemcpyDeviceToDevice, st));
+    if (finish) {
+        k_infer_finish<<<ngp_div_up(n, 256), 256, 0, st>>>(*cfg, opacity, rgb, state, total, total_samples);
+        NGP_CHECK_LAUNCH();
+    }
     return 0;
 }

@@ -153,3 +153,138 @@ __device__ __forceinline__ float march_jitter(float t1, float noise, const March
     if (t1 >= 0.0f) t1 = __fmaf_rn(march_dt(t1, c), noise, t1);
     return t1;
 }
+
+// -------------------------------------------------------------------------------------------------
+// Warp-cooperative marcher (one WARP per ray), bit-exact with the serial one.
+//
+// Every parameter value the reference ever visits lies on the ray's STEP CHAIN
+//     c_0 = t_start,   c_{k+1} = c_k (+) dt(c_k)          ((+) = one fp32 rounded add)
+// because both branches of its loop advance t the same way: an occupied visit does t += dt(t), an empty
+// visit repeats t += dt(t) until t >= t_target. So the marcher is a walk over that chain: at a visited
+// point test the cell; if occupied emit it and go to the next chain point, else jump to the first chain
+// point >= t_target. Here a warp materialises 32 consecutive chain points (31 dependent rounded adds,
+// identical roundings to the serial code), tests all 32 cells at once, and resolves which of them the
+// serial walk would have visited with ballots. One thread per ray is latency bound (a dependent
+// load + ~60 dependent ALU ops per visit, ~2 warps per SM at 8192 rays); this keeps the same
+// sequence of fp32 operations per chain point but runs 32 of them side by side.
+// -------------------------------------------------------------------------------------------------
+struct MarchProbe {
+    bool occ;
+    float dt;        // step at this chain point (the sample's delta)
+    float t_target;  // where an empty visit here jumps to (valid when !occ)
+};
+
+__device__ __forceinline__ MarchProbe march_probe(const MarchRay& r, const MarchConst& c, float t) {
+    MarchProbe o;
+    const float x = __fmaf_rn(r.dx, t, r.ox);
+    const float y = __fmaf_rn(r.dy, t, r.oy);
+    const float z = __fmaf_rn(r.dz, t, r.oz);
+    o.dt = march_dt(t, c);
+    int e_pos, e_dt;
+    frexpf(fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z))), &e_pos);
+    frexpf(__fmul_rn(o.dt, c.gs_f), &e_dt);
+    const int mip = max(min(c.cascades - 1, max(0, e_pos + 1)), min(c.cascades - 1, max(0, e_dt)));
+    const float mip_bound = fminf(scalbnf(1.0f, mip - 1), c.scale);
+    const float mip_bound_inv = __fdiv_rn(1.0f, mip_bound);
+    const float vx = __fmul_rn(__fmul_rn(__fmaf_rn(x, mip_bound_inv, 1.0f), 0.5f), c.gs_f);
+    const float vy = __fmul_rn(__fmul_rn(__fmaf_rn(y, mip_bound_inv, 1.0f), 0.5f), c.gs_f);
+    const float vz = __fmul_rn(__fmul_rn(__fmaf_rn(z, mip_bound_inv, 1.0f), 0.5f), c.gs_f);
+    const int nx = (int)fmaxf(0.0f, fminf(vx, c.gs_m1));
+    const int ny = (int)fmaxf(0.0f, fminf(vy, c.gs_m1));
+    const int nz = (int)fmaxf(0.0f, fminf(vz, c.gs_m1));
+    const uint32_t idx = (uint32_t)mip * c.grid_size3 + morton_encode3((uint32_t)nx, (uint32_t)ny, (uint32_t)nz);
+    o.occ = (__ldg(c.bitfield + (idx >> 3)) >> (idx & 7u)) & 1u;
+    float a;
+    a = __fmaf_rn(r.sx, 0.5f, __fadd_rn((float)nx, 0.5f));
+    a = __fmaf_rn(__fmul_rn(a, c.gs_inv), 2.0f, -1.0f);
+    const float tx = __fmul_rn(__fmaf_rn(mip_bound, a, -x), r.ix);
+    a = __fmaf_rn(r.sy, 0.5f, __fadd_rn((float)ny, 0.5f));
+    a = __fmaf_rn(__fmul_rn(a, c.gs_inv), 2.0f, -1.0f);
+    const float ty = __fmul_rn(__fmaf_rn(mip_bound, a, -y), r.iy);
+    a = __fmaf_rn(r.sz, 0.5f, __fadd_rn((float)nz, 0.5f));
+    a = __fmaf_rn(__fmul_rn(a, c.gs_inv), 2.0f, -1.0f);
+    const float tz = __fmul_rn(__fmaf_rn(mip_bound, a, -z), r.iz);
+    o.t_target = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
+    return o;
+}
+
+// March one ray with a full warp. emit(k, t, dt) is called by the lane owning the k-th sample
+// (k = 0.. in ray order). Returns the number of samples (same in every lane) and leaves in t_resume the
+// chain point the serial marcher would visit next (what raymarching_test stores back into hits_t).
+template <class FEmit>
+__device__ __forceinline__ int march_ray_warp(const MarchRay& ray, const MarchConst& c, float t_start, float t2,
+                                              int max_new, int lane, FEmit emit, float* t_resume = nullptr) {
+    int n = 0;
+    float t = t_start;
+    bool pending = false;   // an empty visit jumped past the end of the previous block
+    float skip_to = 0.f;
+    bool alive = (0.0f <= t) && (t < t2) && (max_new > 0);
+    float resume = t_start;
+    while (alive) {
+        // 1. 32 consecutive chain points: lane j holds c_j
+        float p = t;
+#pragma unroll
+        for (int j = 0; j < 31; ++j) {
+            const float nx = __fadd_rn(p, march_dt(p, c));
+            if (lane > j) p = nx;
+        }
+        float t_next = __fadd_rn(p, march_dt(p, c));
+        t_next = __shfl_sync(0xffffffffu, t_next, 31);
+        // 2. probe all 32 cells
+        const bool valid = p < t2;
+        const MarchProbe pr = march_probe(ray, c, p);
+        const unsigned valid_mask = __ballot_sync(0xffffffffu, valid);
+        const unsigned occ_mask = __ballot_sync(0xffffffffu, valid && pr.occ);
+        // 3. which of them does the serial walk visit?
+        int cur = 0;
+        if (pending) {
+            const unsigned m = __ballot_sync(0xffffffffu, !(p < skip_to));
+            cur = m ? (__ffs(m) - 1) : 32;
+            pending = (m == 0u);
+        }
+        unsigned sample_mask = 0u;
+        while (cur < 32) {
+            if (!((valid_mask >> cur) & 1u)) {  // t >= t2: the ray left the box
+                alive = false;
+                resume = __shfl_sync(0xffffffffu, p, cur);
+                break;
+            }
+            const int room = max_new - n - __popc(sample_mask);
+            if (room <= 0) {  // N_samples reached max_samples
+                alive = false;
+                resume = __shfl_sync(0xffffffffu, p, cur);
+                break;
+            }
+            if ((occ_mask >> cur) & 1u) {
+                // a run of occupied points: each is a sample and the next chain point is visited next
+                const unsigned rest = (~occ_mask) >> cur;
+                int run = rest ? (__ffs(rest) - 1) : (32 - cur);
+                run = min(run, room);
+                const unsigned bits = run >= 32 ? 0xffffffffu : ((1u << run) - 1u);
+                sample_mask |= bits << cur;
+                cur += run;
+            } else {
+                // empty cell: jump to the first chain point that is not below t_target
+                const float tt = __shfl_sync(0xffffffffu, pr.t_target, cur);
+                const unsigned above = cur >= 31 ? 0u : (0xffffffffu << (cur + 1));
+                const unsigned m = __ballot_sync(0xffffffffu, !(p < tt)) & above;
+                if (m) {
+                    cur = __ffs(m) - 1;
+                } else {
+                    cur = 32;
+                    pending = true;
+                    skip_to = tt;
+                }
+            }
+        }
+        if ((sample_mask >> lane) & 1u) emit(n + __popc(sample_mask & ((1u << lane) - 1u)), p, pr.dt);
+        n += __popc(sample_mask);
+        if (alive) {
+            resume = t_next;
+            t = t_next;
+            if (!(t < t2)) alive = false;
+        }
+    }
+    if (t_resume) *t_resume = resume;
+    return n;
+}

@@ -19,7 +19,9 @@ static inline int one_thread_per_ray_block(int n_rays) { return n_rays >= 148 * 
 __global__ void k_train_march(const NgpTrainCfg cfg, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                               const float* __restrict__ noise, const uint8_t* __restrict__ bitfield,
                               float* __restrict__ stage_t, float* __restrict__ stage_dt, int* __restrict__ n_samples) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    // one WARP per ray (march_ray_warp): 32 chain points probed side by side, same t sequence as the serial loop
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (r >= cfg.n_rays) return;
     const MarchConst c = make_march_const(bitfield, cfg.cascades, cfg.grid_size, cfg.max_samples, cfg.scale,
                                           cfg.exp_step_factor, cfg.scale);
@@ -33,20 +35,14 @@ __global__ void k_train_march(const NgpTrainCfg cfg, const float* __restrict__ r
         t2 = tt.y;
     }
     if (t1 >= 0.0f && t1 < cfg.near_distance) t1 = cfg.near_distance;
-    float t = march_jitter(t1, noise[r], c);
-    int n = 0;
-    float x, y, z, dt;
+    const float t = march_jitter(t1, noise[r], c);
     float* st = stage_t + (size_t)r * cfg.max_samples;
     float* sd = stage_dt + (size_t)r * cfg.max_samples;
-    while (0.0f <= t && t < t2 && n < cfg.max_samples) {
-        if (march_visit(ray, c, t, x, y, z, dt)) {
-            st[n] = t;
-            sd[n] = dt;
-            t = __fadd_rn(t, dt);
-            ++n;
-        }
-    }
-    n_samples[r] = n;
+    const int n = march_ray_warp(ray, c, t, t2, cfg.max_samples, lane, [&](int k, float ts, float dts) {
+        st[k] = ts;
+        sd[k] = dts;
+    });
+    if (lane == 0) n_samples[r] = n;
 }
 
 // 3. staging rows -> compact per-sample arrays (one warp per ray, coalesced both ways)
@@ -142,8 +138,7 @@ extern "C" int ngp_render_train_fwd(const NgpNet* net, const NgpTrainCfg* cfg, c
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int n = cfg->n_rays;
-    const int bs = one_thread_per_ray_block(n);
-    k_train_march<<<ngp_div_up(n, bs), bs, 0, st>>>(*cfg, b->rays_o, b->rays_d, b->noise, b->density_bitfield, b->stage_t,
+    k_train_march<<<ngp_div_up((int64_t)n * 32, 128), 128, 0, st>>>(*cfg, b->rays_o, b->rays_d, b->noise, b->density_bitfield, b->stage_t,
                                                      b->stage_dt, b->n_samples);
     NGP_CHECK_LAUNCH();
     size_t temp_bytes = b->scan_temp_bytes;

@@ -54,7 +54,8 @@ def _background(exp_step_factor, device, random_bg=False):
 
 @torch.no_grad()
 def _render_rays_test_fused(model, rays_o, rays_d, hits_t, **kwargs):
-    """Inference through ngp_render_infer: no host synchronisation, one call per image."""
+    """Inference through ngp_render_infer: a device-side wavefront; the host only reads the number of
+    alive rays back once every `rounds_per_check` rounds (the reference synchronises >= 3 times per round)."""
     from .networks import _net_struct
     exp_step_factor = kwargs.get('exp_step_factor', 0.)
     N = rays_o.shape[0]
@@ -83,10 +84,29 @@ def _render_rays_test_fused(model, rays_o, rays_d, hits_t, **kwargs):
         depth = torch.empty(N, device=dev)
         rgb = torch.empty(N, 3, device=dev)
         total = torch.zeros(1, device=dev, dtype=torch.int64)
+        alive = torch.zeros(1, device=dev, dtype=torch.int32)
+        alive_host = getattr(model, '_infer_alive_host', None)
+        if alive_host is None:
+            alive_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            model._infer_alive_host = alive_host
+        st = torch.cuda.current_stream().cuda_stream
+        chunk = int(kwargs.get('rounds_per_check', 8))
+        first = 0
+        while True:
+            # `chunk` rounds are enqueued back to back; the alive count is read back once per chunk
+            rc = L.ngp_render_infer(C.byref(net), C.byref(cfg), rays_o.data_ptr(), rays_d.data_ptr(),
+                                    model.density_bitfield.data_ptr(), opacity.data_ptr(), depth.data_ptr(), rgb.data_ptr(),
+                                    total.data_ptr(), first, chunk, 0, alive.data_ptr(), cache.data_ptr(), cache.numel(), st)
+            _lib.check(rc, "render_infer")
+            first += chunk
+            alive_host.copy_(alive, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            if int(alive_host[0]) == 0 or first > 2 * cfg.sample_budget:
+                break
         rc = L.ngp_render_infer(C.byref(net), C.byref(cfg), rays_o.data_ptr(), rays_d.data_ptr(),
                                 model.density_bitfield.data_ptr(), opacity.data_ptr(), depth.data_ptr(), rgb.data_ptr(),
-                                total.data_ptr(), cache.data_ptr(), cache.numel(), torch.cuda.current_stream().cuda_stream)
-        _lib.check(rc, "render_infer")
+                                total.data_ptr(), first, 0, 1, None, cache.data_ptr(), cache.numel(), st)
+        _lib.check(rc, "render_infer(finish)")
     return {'opacity': opacity, 'depth': depth, 'rgb': rgb, 'total_samples': total[0]}
 
 

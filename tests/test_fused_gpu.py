@@ -218,3 +218,36 @@ def test_training_converges_and_graph_capture_works():
     assert math.isfinite(st["loss"])
     assert st["psnr"] > 22.0, "training PSNR only %.2f dB after 500 steps" % st["psnr"]
     assert int(tr.step_dev) == 500  # the warm-up run inside capture() is rolled back
+
+
+@pytest.mark.parametrize("name", cases.MARCH_CASES)
+def test_warp_marcher_bit_exact_vs_oracle(name, oracle):
+    """the warp-cooperative marcher of the fused path (march_ray_warp) against the serial oracle restatement
+    (itself pinned bit-exactly to the reference kernels by tests/golden): counts, ts, deltas"""
+    import ctypes as C
+    from ngp_pl_b200 import _lib
+    from ngp_pl_b200.models.networks import NGP
+    from ngp_pl_b200.trainer import Trainer
+    c = cases.march_case(name)
+    n = c["o"].shape[0]
+    model = NGP(float(c["scale"])).cuda()
+    with torch.no_grad():
+        model.density_bitfield.copy_(torch.as_tensor(c["bits"]).cuda())
+    tr = Trainer(model, n_rays=n, exp_step_factor=float(c["esf"]))
+    if name == "full":
+        tr.cfg.max_samples = 256  # saturate the per-ray sample cap (the staging stride stays MAX_SAMPLES-safe: 256 <= 1024)
+    tr.set_batch(torch.as_tensor(c["o"]).cuda(), torch.as_tensor(c["d"]).cuda(), torch.zeros(n, 3).cuda())
+    tr.noise.copy_(torch.as_tensor(c["noise"]).cuda())
+    _lib.check(_lib.lib().ngp_render_train_fwd(C.byref(tr.net), C.byref(tr.cfg), C.byref(tr.buf), tr._st()), "fwd")
+    torch.cuda.synchronize()
+    hits = cases.hits_for(c, oracle)
+    ra, xyzs, dirs, deltas, ts = oracle.march_train(c["o"], c["d"], hits, c["bits"], c["cascades"], c["scale"], c["esf"],
+                                                    c["noise"], 128, int(tr.cfg.max_samples))
+    if name == "full":
+        assert ra[:, 2].max() == 256
+    assert (tr.n_samples.cpu().numpy() == ra[:, 2]).all()
+    tot = int(ra[:, 2].sum())
+    assert int(tr.counters[0]) == tot
+    assert (tr.ts[:tot].cpu().numpy().view(np.uint32) == ts.view(np.uint32)).all()
+    assert (tr.deltas[:tot].cpu().numpy().view(np.uint32) == deltas.view(np.uint32)).all()
+    assert (tr.ray_idx[:tot].cpu().numpy() == np.repeat(np.arange(n), ra[:, 2])).all()

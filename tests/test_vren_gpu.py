@@ -76,7 +76,16 @@ def test_aabb_and_march_train_vs_oracle(name, oracle):
     bits_equal(xyzs[:total].cpu().numpy(), xyz_o, "xyzs")
     bits_equal(dirs[:total].cpu().numpy(), dir_o, "dirs")
     if name == "full":
-        assert ra_o[:, 2].max() == 1024  # max_samples saturation is exercised
+        # max_samples saturation: a fully occupied grid with a small sample cap (also moves the dt lower bound)
+        out = vren.raymarching_train(T(c["o"]), T(c["d"]), hits, T(c["bits"]), c["cascades"], float(c["scale"]), float(c["esf"]),
+                                     T(c["noise"]), 128, 256)
+        ra2, xyz2, dir2, dl2, ts2 = oracle.march_train(c["o"], c["d"], hits_o, c["bits"], c["cascades"], c["scale"], c["esf"],
+                                                      c["noise"], 128, 256)
+        assert ra2[:, 2].max() == 256 and (ra2[:, 2] == 256).sum() > 4
+        assert (out[0].cpu().numpy() == ra2).all()
+        tot2 = int(out[5][0])
+        bits_equal(out[4][:tot2].cpu().numpy(), ts2, "ts (saturated)")
+        bits_equal(out[3][:tot2].cpu().numpy(), dl2, "deltas (saturated)")
 
 
 @pytest.mark.parametrize("name", cases.MARCH_CASES)
@@ -239,16 +248,17 @@ def test_distortion_loss(oracle, ref):
     o_loss, o_wi, o_wti = oracle.distortion_fw(ws_np, c["deltas"], c["ts"], c["rays_a"])
     rel_close(wi.cpu().numpy(), o_wi, atol=1e-7, what="ws_inclusive_scan")
     rel_close(wti.cpu().numpy(), o_wti, atol=1e-7, what="wts_inclusive_scan")
-    rel_close(loss.cpu().numpy(), o_loss, atol=1e-6, what="distortion loss")
+    # the per-ray loss is a difference of O(1) prefix products: absolute, not relative, accuracy
+    rel_close(loss.cpu().numpy(), o_loss, atol=3e-5, what="distortion loss")
     dL = np.random.RandomState(8).normal(size=ra.shape[0]).astype(np.float32)
     dws = vren.distortion_loss_bw(T(dL), wi, wti, ws, dl, ts, ra)
     o_dws = oracle.distortion_bw(dL, o_wi, o_wti, ws_np, c["deltas"], c["ts"], c["rays_a"])
-    rel_close(dws.cpu().numpy(), o_dws, atol=2e-6, what="dL_dws")
+    rel_close(dws.cpu().numpy(), o_dws, atol=3e-5, what="dL_dws")
     if ref is not None:
         r_loss, r_wi, r_wti = ref.vren.distortion_loss_fw(ws, dl, ts, ra)
-        rel_close(loss.cpu().numpy(), r_loss.cpu().numpy(), atol=1e-6, what="distortion loss vs reference")
+        rel_close(loss.cpu().numpy(), r_loss.cpu().numpy(), atol=3e-5, what="distortion loss vs reference")
         r_dws = ref.vren.distortion_loss_bw(T(dL), r_wi, r_wti, ws, dl, ts, ra)
-        rel_close(dws.cpu().numpy(), r_dws.cpu().numpy(), atol=2e-6, what="dL_dws vs reference")
+        rel_close(dws.cpu().numpy(), r_dws.cpu().numpy(), atol=3e-5, what="dL_dws vs reference")
 
 
 def test_packbits_morton(oracle, ref):
