@@ -51,39 +51,63 @@ def parse():
 
 # --------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe). Started
+    early (nvidia-smi takes ~1 s to produce its first row); rows are time-stamped and only those inside
+    [mark_begin(), mark_end()] are summarised."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, period_ms=20):
         super().__init__(daemon=True)
-        self.index = index
+        self.index, self.period = index, period_ms
         self.rows = []
         self.proc = None
+        self.t0 = self.t1 = None
 
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
+                self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
         except Exception:
             pass
+
+    def wait_first_row(self, timeout=5.0):
+        t = time.time()
+        while not self.rows and time.time() - t < timeout:
+            time.sleep(0.05)
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is not None:
             self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        rows = [r for (t, r) in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or 1e30) + 0.05]
+        in_region = len(rows)
+        if not rows:  # region shorter than one sampling period: take the rows closest to it
+            rows = [r for (_, r) in self.rows[-3:]]
+
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+        sm = [num(r[1]) for r in rows if len(r) > 2 and num(r[1]) is not None]
+        mx = [num(r[2]) for r in rows if len(r) > 2 and num(r[2]) is not None]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             for nm, v in zip(names, r[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": in_region}
 
 
 def dist_setup(args):
@@ -177,6 +201,8 @@ def run_b200(args):
     tr.attach_bank(bank)
     pretrain = args.pretrain if args.pretrain is not None else 1000
     K, W = args.steps, max(args.warmup, 3)
+    sampler = ClockSampler(local)
+    sampler.start()
 
     # graphs: single GPU = one graph per step; multi GPU = [fwd+bwd] graph, eager NCCL all-reduce, [Adam] graph
     if world == 1:
@@ -189,16 +215,16 @@ def run_b200(args):
     for _ in range(W):
         step()
     barrier(world)
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.3)
+    sampler.wait_first_row()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(world)
+    sampler.mark_begin()
     e0.record()
     for _ in range(K):
         step()
     e1.record()
     barrier(world)
+    sampler.mark_end()
     ms = max_over_ranks(e0.elapsed_time(e1), world)
     clocks = sampler.stop()
     stats = tr.stats()
@@ -413,19 +439,21 @@ def run_reference(args):
         state["res"] = (res, rgb)
     pretrain = args.pretrain if args.pretrain is not None else 1000
     K, W = args.steps, max(args.warmup, 3)
+    sampler = ClockSampler(0)
+    sampler.start()
     for _ in range(pretrain + W):
         step()
     torch.cuda.synchronize()
-    sampler = ClockSampler(0)
-    sampler.start()
-    time.sleep(0.3)
+    sampler.wait_first_row()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    sampler.mark_begin()
     e0.record()
     for _ in range(K):
         step()
     e1.record()
     torch.cuda.synchronize()
+    sampler.mark_end()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
     res, rgb = state["res"]

@@ -8,6 +8,7 @@
 #include "mlp.cuh"
 #include "../../include/ngp_b200.h"
 #include <math.h>
+#include <stdlib.h>
 
 extern "C" int ngp_abi_version(void) { return NGP_ABI_VERSION; }
 
@@ -156,10 +157,8 @@ __device__ __forceinline__ float hi_half(uint32_t u) { return __half2float(__ush
 // -------------------------------------------------------------------------------------------------
 // forward
 // -------------------------------------------------------------------------------------------------
-#define FWD_THREADS 256
-#define FWD_MT 2
-
-__global__ void __launch_bounds__(FWD_THREADS, 1)
+template <int FWD_MT, int FWD_THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(FWD_THREADS, MIN_BLOCKS)
 k_ngp_fwd(const NgpNet net, const NgpSamples smp, const int want_rgb, float* __restrict__ sigmas, float* __restrict__ rgbs,
           __half* __restrict__ h_out, uint4* __restrict__ feat_save) {
     __shared__ MlpWeightsFwd sw;
@@ -277,16 +276,40 @@ k_ngp_fwd(const NgpNet net, const NgpSamples smp, const int want_rgb, float* __r
     }
 }
 
+template <int MT, int THREADS, int MIN_BLOCKS>
+static int launch_fwd(const NgpNet* net, const NgpSamples* smp, int want_rgb, float* sigmas, float* rgbs, uint16_t* h_out,
+                      void* feat_save, cudaStream_t st) {
+    const int64_t n_tiles = (smp->n + 16 * MT - 1) / (16 * MT);
+    const int64_t want = (n_tiles + THREADS / 32 - 1) / (THREADS / 32);
+    const int64_t cap = (int64_t)ngp_sm_count() * MIN_BLOCKS;
+    const int grid = (int)(want < cap ? want : cap);
+    k_ngp_fwd<MT, THREADS, MIN_BLOCKS><<<grid, THREADS, 0, st>>>(*net, *smp, want_rgb, sigmas, rgbs, (__half*)h_out,
+                                                                 (uint4*)feat_save);
+    return 0;
+}
+
+// NGP_FWD_VARIANT (env, read once) selects the tile/occupancy variant; the default is the measured best.
+static int fwd_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("NGP_FWD_VARIANT");
+        v = e ? atoi(e) : 3;
+    }
+    return v;
+}
+
 extern "C" int ngp_net_forward(const NgpNet* net, const NgpSamples* smp, int want_rgb, float* sigmas, float* rgbs,
                                uint16_t* h_out, void* feat_save, void* stream) {
     if (!net || !smp || smp->n < 0 || !sigmas || (want_rgb && !rgbs)) return NGP_EINVAL;
     if (net->meta.n_levels < 1 || net->meta.n_levels > NGP_MAX_LEVELS) return NGP_EINVAL;
     if (smp->n == 0) return 0;
-    const int64_t n_tiles = (smp->n + 16 * FWD_MT - 1) / (16 * FWD_MT);
-    const int64_t want = (n_tiles + FWD_THREADS / 32 - 1) / (FWD_THREADS / 32);
-    const int grid = (int)(want < (int64_t)ngp_sm_count() ? want : ngp_sm_count());
-    k_ngp_fwd<<<grid, FWD_THREADS, 0, (cudaStream_t)stream>>>(*net, *smp, want_rgb, sigmas, rgbs, (__half*)h_out,
-                                                              (uint4*)feat_save);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (fwd_variant()) {
+        case 0: launch_fwd<2, 256, 1>(net, smp, want_rgb, sigmas, rgbs, h_out, feat_save, st); break;   // 32 samples/warp, 8 warps/SM
+        case 2: launch_fwd<1, 128, 5>(net, smp, want_rgb, sigmas, rgbs, h_out, feat_save, st); break;   // 16 samples/warp, 20 warps/SM
+        case 3: launch_fwd<1, 256, 3>(net, smp, want_rgb, sigmas, rgbs, h_out, feat_save, st); break;   // 16 samples/warp, 24 warps/SM
+        default: launch_fwd<1, 256, 2>(net, smp, want_rgb, sigmas, rgbs, h_out, feat_save, st); break;  // 16 samples/warp, 16 warps/SM
+    }
     NGP_CHECK_LAUNCH();
     return 0;
 }

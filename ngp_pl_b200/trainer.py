@@ -24,6 +24,30 @@ from .models.networks import NGP, feat_save_bytes
 from .models.rendering import MAX_SAMPLES, NEAR_DISTANCE
 
 
+def allreduce_gradients(flat_grad, world_size, process_group=None):
+    """The ONE collective of a data-parallel step: SUM all-reduce of the flat gradient buffer (the 1/N of
+    DDP's mean is applied by the Adam kernel's grad_mul). Backend-agnostic (NCCL on GPUs, gloo in the CPU tests)."""
+    if world_size > 1:
+        import torch.distributed as dist
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=process_group)
+    return flat_grad
+
+
+def broadcast_occupancy(density_bitfield, world_size, process_group=None, src=0):
+    """Occupancy policy: all ranks march rank `src`'s bitfield (the reference leaves this to DDP buffer sync)."""
+    if world_size > 1:
+        import torch.distributed as dist
+        dist.broadcast(density_bitfield, src=src, group=process_group)
+    return density_bitfield
+
+
+def shard_range(n_items, world_size, rank):
+    """contiguous shard [lo, hi) of n_items (test views / image rows) for `rank`; sizes differ by at most one"""
+    base, extra = divmod(n_items, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
 class Trainer:
     def __init__(self, model: NGP, n_rays=8192, lr=1e-2, exp_step_factor=0.0, bg=(1.0, 1.0, 1.0), lambda_opacity=1e-3,
                  T_threshold=1e-4, betas=(0.9, 0.999), eps=1e-15, max_total_samples=None, update_interval=16,
@@ -164,9 +188,7 @@ class Trainer:
                 (self.seed * 2654435761 + self.host_step * 40503 + 12345) & 0xffffffff,
                 self.grid_ws.data_ptr(), self.grid_ws.numel(), self._st())
             _lib.check(rc, "update_density_grid")
-            if self.world_size > 1:
-                import torch.distributed as dist
-                dist.broadcast(m.density_bitfield, src=0, group=self.pg)
+            broadcast_occupancy(m.density_bitfield, self.world_size, self.pg)
 
     # ---- pieces of one step (all asynchronous) -------------------------------------------------------------
     def attach_bank(self, bank):
@@ -205,9 +227,7 @@ class Trainer:
                                           self.G[self.n_enc:].data_ptr(), self._st()), "render_train_bwd")
 
     def allreduce(self):
-        if self.world_size > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.G, op=dist.ReduceOp.SUM, group=self.pg)
+        allreduce_gradients(self.G, self.world_size, self.pg)
 
     def optimizer_step(self):
         rc = _lib.lib().ngp_adam_step(self.P.data_ptr(), self.G.data_ptr(), self.M.data_ptr(), self.V.data_ptr(),

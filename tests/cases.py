@@ -51,6 +51,12 @@ def march_case(name):
         bits = np.full(128 ** 3 // 8, 255, np.uint8)  # saturates max_samples on the diagonal
         o, d = rays_from_scene(sc, 32, 13)
         esf = 0.0
+    elif name == "full_scale2":
+        # scale 2 => 3 cascades, chords several units long at the minimum step: saturates max_samples = 1024
+        sc = synth.Scene(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), 2.0, 0.0)
+        bits = np.full(sc.cascades * 128 ** 3 // 8, 255, np.uint8)
+        o, d = rays_from_scene(sc, 32, 15)
+        esf = 0.0
     elif name == "mip360":
         sc = synth.mip360_scene(0)
         bits = synth.pack_bits(synth.occupancy_grid(sc))
@@ -64,7 +70,7 @@ def march_case(name):
                 esf=np.float32(esf), grid_size=128, max_samples=1024)
 
 
-MARCH_CASES = ["lego", "lego_half_random", "full", "mip360"]
+MARCH_CASES = ["lego", "lego_half_random", "full", "full_scale2", "mip360"]
 
 
 def composite_case(seed=3, n_rays=96, max_n=300):

@@ -75,17 +75,8 @@ def test_aabb_and_march_train_vs_oracle(name, oracle):
     bits_equal(deltas[:total].cpu().numpy(), dl_o, "deltas")
     bits_equal(xyzs[:total].cpu().numpy(), xyz_o, "xyzs")
     bits_equal(dirs[:total].cpu().numpy(), dir_o, "dirs")
-    if name == "full":
-        # max_samples saturation: a fully occupied grid with a small sample cap (also moves the dt lower bound)
-        out = vren.raymarching_train(T(c["o"]), T(c["d"]), hits, T(c["bits"]), c["cascades"], float(c["scale"]), float(c["esf"]),
-                                     T(c["noise"]), 128, 256)
-        ra2, xyz2, dir2, dl2, ts2 = oracle.march_train(c["o"], c["d"], hits_o, c["bits"], c["cascades"], c["scale"], c["esf"],
-                                                      c["noise"], 128, 256)
-        assert ra2[:, 2].max() == 256 and (ra2[:, 2] == 256).sum() > 4
-        assert (out[0].cpu().numpy() == ra2).all()
-        tot2 = int(out[5][0])
-        bits_equal(out[4][:tot2].cpu().numpy(), ts2, "ts (saturated)")
-        bits_equal(out[3][:tot2].cpu().numpy(), dl2, "deltas (saturated)")
+    if name == "full_scale2":
+        assert ra_o[:, 2].max() == 1024 and (ra_o[:, 2] == 1024).sum() >= 4  # max_samples saturation is exercised
 
 
 @pytest.mark.parametrize("name", cases.MARCH_CASES)

@@ -64,6 +64,10 @@ def main():
     L = _lib.lib()
     out["net_fwd_ms"] = timeit(lambda: L.ngp_net_forward(C.byref(net), C.byref(smp), 1, sig.data_ptr(), rgb.data_ptr(), None, feat.data_ptr(), st), flush=flush)
     out["net_fwd_nosave_ms"] = timeit(lambda: L.ngp_net_forward(C.byref(net), C.byref(smp), 1, sig.data_ptr(), rgb.data_ptr(), None, None, st), flush=flush)
+    if "--fwd-only" in sys.argv:
+        print(json.dumps({"variant": os.environ.get("NGP_FWD_VARIANT", "default"), "samples": n, "net_fwd_ms": out["net_fwd_ms"],
+                          "net_fwd_nosave_ms": out["net_fwd_nosave_ms"]}))
+        return
     out["net_density_ms"] = timeit(lambda: L.ngp_net_forward(C.byref(net), C.byref(smp), 0, sig.data_ptr(), None, None, None, st), flush=flush)
     dsig = torch.randn(n, device=dev) * 1e-3; drgb = torch.randn(n, 3, device=dev) * 1e-2
     ge = torch.zeros_like(model.xyz_encoder.params); gr = torch.zeros_like(model.rgb_net.params)
@@ -80,7 +84,7 @@ def main():
     sigb = torch.empty(n_big, device=dev); rgbb = torch.empty(n_big, 3, device=dev)
     out["net_fwd_4M_random_ms"] = timeit(lambda: L.ngp_net_forward(C.byref(net), C.byref(smpb), 1, sigb.data_ptr(), rgbb.data_ptr(), None, None, st), iters=5, warm=2, flush=flush)
     print(json.dumps(out, indent=1))
-    if len(sys.argv) > 1:
+    if len(sys.argv) > 1 and not sys.argv[1].startswith("--"):
         os.makedirs(os.path.dirname(sys.argv[1]) or ".", exist_ok=True)
         json.dump(out, open(sys.argv[1], "w"), indent=1)
 
