@@ -286,7 +286,7 @@ def run_b200(args):
         st = torch.cuda.current_stream().cuda_stream
         t_bwd = timed(lambda: L.ngp_net_backward(C.byref(tr.net), C.byref(smp), tr.dsigmas.data_ptr(), tr.drgbs.data_ptr(),
                                                  tr.feat_save.data_ptr(), tr.scalars[1:].data_ptr(), tr.G.data_ptr(),
-                                                 tr.G[tr.n_enc:].data_ptr(), None, 0, st))
+                                                 tr.G[tr.n_enc:].data_ptr(), tr.bwd_ws.data_ptr(), tr.bwd_ws.numel(), st))
         t_fwd = timed(lambda: L.ngp_net_forward(C.byref(tr.net), C.byref(smp), 1, tr.sigmas.data_ptr(), tr.rgbs.data_ptr(),
                                                 None, tr.feat_save.data_ptr(), st))
         tr.G.zero_()

@@ -148,12 +148,15 @@ typedef struct {
 int ngp_net_forward(const NgpNet* net, const NgpSamples* smp, int want_rgb, float* sigmas, float* rgbs,
                     uint16_t* h_out /* optional fp16 (n,16) */, void* feat_save /* 16-B aligned */, void* stream);
 
-size_t ngp_net_backward_workspace(void);
+size_t ngp_net_backward_workspace(int64_t n); /* 64 B per sample: feature gradients [level][sample] */
 /* Fused backward: recomputes the MLP activations from feat_save (or by re-gathering when NULL),
  * back-propagates dL/dsigmas (n) and dL/drgbs (n,3), accumulates
  *   grad_enc (fp32, same layout as xyz_encoder.params) and grad_rgb (fp32, 7168)   with atomics (+=).
  * loss_scale (device float*, optional) is the power-of-two the fp16 gradient operands are scaled by
- * internally (results are un-scaled); NULL = 1. */
+ * internally (results are un-scaled); NULL = 1. Two kernels: the MLP backward (dgrad + wgrad on tensor
+ * cores) writes the feature gradients to `workspace`; the scatter kernel (one thread per sample and level,
+ * duplicate cells merged inside the warp) turns them into vector reductions on the table gradient.
+ * With smp->n_dev the workspace must cover the capacity smp->n. */
 int ngp_net_backward(const NgpNet* net, const NgpSamples* smp, const float* dL_dsigmas, const float* dL_drgbs,
                      const void* feat_save, const float* loss_scale, float* grad_enc, float* grad_rgb,
                      void* workspace, size_t workspace_bytes, void* stream);
@@ -205,6 +208,8 @@ typedef struct {
     float* scalars;               /* [0] amax scratch, [1] loss scale, [2] sum sq err, [3] sum opacity entropy */
     void* scan_temp;
     size_t scan_temp_bytes;
+    void* bwd_workspace;          /* ngp_net_backward_workspace(max_total_samples) bytes */
+    size_t bwd_workspace_bytes;
 } NgpTrainBuffers;
 
 size_t ngp_train_scan_temp_bytes(int n_rays);

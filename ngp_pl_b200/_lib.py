@@ -93,7 +93,7 @@ class NgpTrainBuffers(C.Structure):
         "rays_o", "rays_d", "noise", "density_bitfield",
         "stage_t", "stage_dt", "n_samples", "offsets", "counters", "rgb", "opacity", "depth",
         "ray_idx", "ts", "deltas", "sigmas", "rgbs", "ws", "dsigmas", "drgbs", "feat_save", "scalars",
-        "scan_temp")] + [("scan_temp_bytes", C.c_size_t)]
+        "scan_temp")] + [("scan_temp_bytes", C.c_size_t), ("bwd_workspace", C.c_void_p), ("bwd_workspace_bytes", C.c_size_t)]
 
 
 _P = C.c_void_p
@@ -122,7 +122,7 @@ SIGNATURES = {
     "ngp_grid_meta": (C.c_uint32, [_i, _i, _i, _f, C.POINTER(NgpGridMeta)]),
     "ngp_cast_params": (_i, [_P, _P, _i64, _P]),
     "ngp_net_forward": (_i, [C.POINTER(NgpNet), C.POINTER(NgpSamples), _i, _P, _P, _P, _P, _P]),
-    "ngp_net_backward_workspace": (_sz, []),
+    "ngp_net_backward_workspace": (_sz, [_i64]),
     "ngp_net_backward": (_i, [C.POINTER(NgpNet), C.POINTER(NgpSamples), _P, _P, _P, _P, _P, _P, _P, _sz, _P]),
     "ngp_grad_scale": (_i, [_P, _P, _P, _i64, _P, _P, _P]),
     "ngp_train_scan_temp_bytes": (_sz, [_i]),

@@ -394,7 +394,7 @@ __device__ __forceinline__ WgradTile wgrad_tile_of(int t) {
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 k_ngp_bwd(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_dsigmas, const float* __restrict__ dL_drgbs,
           const uint4* __restrict__ feat_save, const float* __restrict__ loss_scale, float* __restrict__ grad_enc,
-          float* __restrict__ grad_rgb) {
+          float* __restrict__ grad_rgb, uint32_t* __restrict__ dfeat, const int64_t dfeat_stride) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BwdSmem& S = *reinterpret_cast<BwdSmem*>(smem_raw);
     const __half* wd = reinterpret_cast<const __half*>(net.enc_params_h);
@@ -403,7 +403,6 @@ k_ngp_bwd(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_d
     load_weights_bwd(S.wb, wd, wr, threadIdx.x, BWD_THREADS);
     __syncthreads();
     const uint32_t* table = reinterpret_cast<const uint32_t*>(wd + NGP_DENSITY_MLP_PARAMS);
-    float* grad_table = grad_enc + NGP_DENSITY_MLP_PARAMS;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
     const int64_t n = sample_count(smp);
@@ -430,6 +429,22 @@ k_ngp_bwd(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_d
             valid[0][h] = row < n;
             sm[0][h] = load_sample(smp, row, valid[0][h]);
             to_unit(net, sm[0][h], u[0][h][0], u[0][h][1], u[0][h][2]);
+        }
+
+        // upstream gradients of this lane's rows: issued now, consumed after the forward recompute
+        float up_sig[2] = {0.f, 0.f}, up_c0[2] = {0.f, 0.f}, up_c1[2] = {0.f, 0.f};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t row = base + g + 8 * h;
+            if (valid[0][h]) {
+                if (q == 0) {
+                    up_sig[h] = __ldg(dL_dsigmas + row);
+                    up_c0[h] = __ldg(dL_drgbs + 3 * row);
+                    up_c1[h] = __ldg(dL_drgbs + 3 * row + 1);
+                } else if (q == 1) {
+                    up_c0[h] = __ldg(dL_drgbs + 3 * row + 2);
+                }
+            }
         }
 
         // ---- recompute the forward activations ----
@@ -492,12 +507,8 @@ k_ngp_bwd(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_d
                     s0 = o0 * (1.0f - o0);
                     s1 = o1 * (1.0f - o1);
                 }
-                if (q == 0) {
-                    d0 = __ldg(dL_drgbs + 3 * row) * s0 * scale;
-                    d1 = __ldg(dL_drgbs + 3 * row + 1) * s1 * scale;
-                } else {
-                    d0 = __ldg(dL_drgbs + 3 * row + 2) * s0 * scale;
-                }
+                d0 = up_c0[h] * s0 * scale;
+                d1 = (q == 0) ? up_c1[h] * s1 * scale : 0.f;
             }
             doutA[0][0][h] = pack_half2(d0, d1);
         }
@@ -527,7 +538,7 @@ k_ngp_bwd(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_d
                     const int64_t row = base + g + 8 * h;
                     if (valid[0][h]) {
                         const float h0 = lo_half(hA[0][0][h]);
-                        c[0][0][2 * h] += __ldg(dL_dsigmas + row) * expf(fminf(fmaxf(h0, -15.f), 15.f)) * scale;
+                        c[0][0][2 * h] += up_sig[h] * expf(fminf(fmaxf(h0, -15.f), 15.f)) * scale;
                     }
                 }
             }
@@ -539,19 +550,20 @@ k_ngp_bwd(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_d
             mlp_layer<1, 16, 64, LD16>(dhA, S.wb.w2dT, c, g, q);
             relu_bwd_to_frag<1, 64>(c, hidA, dhidA);
         }
-        // ---- gradient of the encoded features, scattered straight into the fp32 table gradient ----
+        // ---- gradient of the encoded features (still multiplied by the loss scale), stored [level][sample] as
+        //      half2 for the scatter kernel: lanes with equal q write 8 consecutive samples = one full sector ----
         {
             float c[1][4][4];
             mlp_layer<1, 64, 32, LD64>(dhidA, S.wb.w1dT, c, g, q);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
+                const int64_t row = base + g + 8 * h;
                 if (!valid[0][h]) continue;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int level = 4 * j + q;
                     if (level < net.meta.n_levels)
-                        grid_scatter(grad_table, net.meta, level, u[0][h][0], u[0][h][1], u[0][h][2],
-                                     c[0][j][2 * h] * inv_scale, c[0][j][2 * h + 1] * inv_scale);
+                        dfeat[(int64_t)level * dfeat_stride + row] = pack_half2(c[0][j][2 * h], c[0][j][2 * h + 1]);
                 }
             }
         }
@@ -599,25 +611,112 @@ k_ngp_bwd(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_d
     }
 }
 
-extern "C" size_t ngp_net_backward_workspace(void) { return 0; }
+// -------------------------------------------------------------------------------------------------
+// hash-table gradient scatter: one thread per (sample, level), a warp = 32 CONSECUTIVE samples of one
+// level. Consecutive samples of a ray fall into the same cell at the coarse levels, so equal cells are
+// contiguous lane runs: their 16 corner contributions are summed with a segmented shuffle reduction and
+// only the head of each run issues the 8 vector reductions (fewer, and far less contended, L2 atomics).
+// -------------------------------------------------------------------------------------------------
+#define SCATTER_THREADS 256
+__global__ void __launch_bounds__(SCATTER_THREADS)
+k_grid_scatter_merged(const NgpNet net, const NgpSamples smp, const uint32_t* __restrict__ dfeat, const int64_t dfeat_stride,
+                      const float* __restrict__ loss_scale, float* __restrict__ grad_table) {
+    const int level = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int64_t n = sample_count(smp);
+    const float inv_scale = loss_scale ? 1.0f / *loss_scale : 1.0f;
+    const uint32_t res = net.meta.res[level];
+    const uint32_t off = net.meta.offset[level];
+    const uint32_t entries = net.meta.offset[level + 1] - off;
+    const bool hashed = (net.meta.hashed_mask >> level) & 1u;
+    const float scale = net.meta.scale[level];
+    const uint32_t* df = dfeat + (int64_t)level * dfeat_stride;
+    const int64_t n_pad = (n + 31) & ~(int64_t)31;
+
+    for (int64_t s = blockIdx.x * (int64_t)SCATTER_THREADS + threadIdx.x; s < n_pad; s += (int64_t)gridDim.x * SCATTER_THREADS) {
+        const bool valid = s < n;
+        const SampleIn sm = load_sample(smp, s, valid);
+        float u, v, w;
+        to_unit(net, sm, u, v, w);
+        const GridCell c = grid_cell(u, v, w, scale);
+        float2 gr = make_float2(0.f, 0.f);
+        if (valid) {
+            gr = unpack_half2(__ldg(df + s));
+            gr.x *= inv_scale;
+            gr.y *= inv_scale;
+        }
+        // corner contributions of this sample
+        float acc[16];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float wk = ((k & 1) ? c.wx : 1.0f - c.wx) * ((k & 2) ? c.wy : 1.0f - c.wy) * ((k & 4) ? c.wz : 1.0f - c.wz);
+            acc[2 * k] = wk * gr.x;
+            acc[2 * k + 1] = wk * gr.y;
+        }
+        // runs of equal cells (an invalid lane never joins a run)
+        const uint32_t px = __shfl_up_sync(0xffffffffu, c.gx, 1), py = __shfl_up_sync(0xffffffffu, c.gy, 1),
+                       pz = __shfl_up_sync(0xffffffffu, c.gz, 1);
+        const bool pvalid = __shfl_up_sync(0xffffffffu, valid ? 1 : 0, 1) != 0;
+        const bool head = lane == 0 || !valid || !pvalid || px != c.gx || py != c.gy || pz != c.gz;
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        if (heads != 0xffffffffu) {
+            // last lane of my run = lane before the next head
+            const unsigned later = lane == 31 ? 0u : (heads >> (lane + 1));
+            const int run_end = later ? lane + __ffs(later) - 1 : 31;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const bool take = lane + d <= run_end;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const float o = __shfl_down_sync(0xffffffffu, acc[k], d);
+                    if (take) acc[k] += o;
+                }
+            }
+        }
+        if (valid && head) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t qx = c.gx + (k & 1), qy = c.gy + ((k >> 1) & 1), qz = c.gz + ((k >> 2) & 1);
+                const uint32_t idx = off + grid_corner_index(qx, qy, qz, res, entries, hashed);
+                red_add_f32x2(grad_table + 2 * (size_t)idx, acc[2 * k], acc[2 * k + 1]);
+            }
+        }
+    }
+}
+
+// workspace of ngp_net_backward: the feature gradients, one half2 per (level, sample): 64 B per sample
+extern "C" size_t ngp_net_backward_workspace(int64_t n) {
+    if (n < 0) return 0;
+    const int64_t n16 = (n + 15) / 16 * 16;
+    return (size_t)n16 * NGP_MAX_LEVELS * sizeof(uint32_t);
+}
 
 extern "C" int ngp_net_backward(const NgpNet* net, const NgpSamples* smp, const float* dL_dsigmas, const float* dL_drgbs,
                                 const void* feat_save, const float* loss_scale, float* grad_enc, float* grad_rgb,
                                 void* workspace, size_t workspace_bytes, void* stream) {
-    (void)workspace; (void)workspace_bytes;
     if (!net || !smp || smp->n < 0 || !dL_dsigmas || !dL_drgbs || !grad_enc || !grad_rgb) return NGP_EINVAL;
     if (net->meta.n_levels < 1 || net->meta.n_levels > NGP_MAX_LEVELS) return NGP_EINVAL;
     if (smp->n == 0) return 0;
+    if (!workspace || workspace_bytes < ngp_net_backward_workspace(smp->n)) return NGP_EINVAL;
     static bool attr_set = false;
     if (!attr_set) {
         NGP_CUDA(cudaFuncSetAttribute(k_ngp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
         attr_set = true;
     }
+    cudaStream_t st = (cudaStream_t)stream;
     const int64_t n_mtiles = (smp->n + 15) / 16;
     const int64_t n_blks = (n_mtiles + BWD_WARPS - 1) / BWD_WARPS;
     const int grid = (int)(n_blks < (int64_t)ngp_sm_count() ? n_blks : ngp_sm_count());
-    k_ngp_bwd<<<grid, BWD_THREADS, sizeof(BwdSmem), (cudaStream_t)stream>>>(
-        *net, *smp, dL_dsigmas, dL_drgbs, (const uint4*)feat_save, loss_scale, grad_enc, grad_rgb);
+    const int64_t stride = n_mtiles * 16;
+    k_ngp_bwd<<<grid, BWD_THREADS, sizeof(BwdSmem), st>>>(*net, *smp, dL_dsigmas, dL_drgbs, (const uint4*)feat_save,
+                                                          loss_scale, grad_enc, grad_rgb, (uint32_t*)workspace, stride);
+    NGP_CHECK_LAUNCH();
+    int64_t gx = (smp->n + SCATTER_THREADS - 1) / SCATTER_THREADS;
+    const int64_t cap = (int64_t)ngp_sm_count() * 8 / net->meta.n_levels + 1;
+    if (gx > cap) gx = cap;
+    dim3 sg((unsigned)gx, (unsigned)net->meta.n_levels);
+    k_grid_scatter_merged<<<sg, SCATTER_THREADS, 0, st>>>(*net, *smp, (const uint32_t*)workspace, stride, loss_scale,
+                                                          grad_enc + NGP_DENSITY_MLP_PARAMS);
     NGP_CHECK_LAUNCH();
     return 0;
 }

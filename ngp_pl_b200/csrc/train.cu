@@ -237,8 +237,8 @@ extern "C" int ngp_render_train_bwd(const NgpNet* net, const NgpTrainCfg* cfg, c
     k_train_grad_scale<<<1, 1, 0, st>>>(b->scalars);
     NGP_CHECK_LAUNCH();
     const NgpSamples smp = train_samples(cfg, b);
-    return ngp_net_backward(net, &smp, b->dsigmas, b->drgbs, b->feat_save, b->scalars + 1, grad_enc, grad_rgb, nullptr, 0,
-                            stream);
+    return ngp_net_backward(net, &smp, b->dsigmas, b->drgbs, b->feat_save, b->scalars + 1, grad_enc, grad_rgb,
+                            b->bwd_workspace, b->bwd_workspace_bytes, stream);
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -95,9 +95,12 @@ class _NGPForward(torch.autograd.Function):
                 L = _lib.lib()
                 _lib.check(L.ngp_grad_scale(dL_dsig.data_ptr(), sig.data_ptr(), dL_drgb.data_ptr(), n,
                                             scratch.data_ptr(), scratch[1:].data_ptr(), _st()), "grad_scale")
+                ws_bytes = L.ngp_net_backward_workspace(n)
+                ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
                 rc = L.ngp_net_backward(C.byref(net), C.byref(smp), dL_dsig.data_ptr(), dL_drgb.data_ptr(),
                                         ctx.feat.data_ptr() if ctx.feat is not None else None,
-                                        scratch[1:].data_ptr(), g_enc.data_ptr(), g_rgb.data_ptr(), None, 0, _st())
+                                        scratch[1:].data_ptr(), g_enc.data_ptr(), g_rgb.data_ptr(), ws.data_ptr(), ws_bytes,
+                                        _st())
                 _lib.check(rc, "net_backward")
         return None, None, g_enc, g_rgb, None
 

@@ -158,6 +158,10 @@ class Trainer:
             b.ws = self.ws.data_ptr() if self.ws is not None else None
             b.density_bitfield = model.density_bitfield.data_ptr()
             b.scan_temp_bytes = scan_bytes
+            bwd_bytes = L.ngp_net_backward_workspace(cap)
+            self.bwd_ws = torch.empty(bwd_bytes, device=dev, dtype=torch.uint8)
+            b.bwd_workspace = self.bwd_ws.data_ptr()
+            b.bwd_workspace_bytes = bwd_bytes
             self.buf = b
 
             # ---- occupancy grid ----------------------------------------------------------------------------

@@ -144,11 +144,12 @@ def test_backward_recompute_matches_saved_features():
     dsig = torch.randn(n, device="cuda") * 1e-3
     drgb = torch.randn(n, 3, device="cuda") * 1e-2
     outs = []
+    ws = torch.empty(L.ngp_net_backward_workspace(n), device="cuda", dtype=torch.uint8)
     for fs in (feat.data_ptr(), None):
         ge = torch.zeros_like(model.xyz_encoder.params)
         gr = torch.zeros_like(model.rgb_net.params)
         _lib.check(L.ngp_net_backward(C.byref(net), C.byref(smp), dsig.data_ptr(), drgb.data_ptr(), fs, None,
-                                      ge.data_ptr(), gr.data_ptr(), None, 0, st), "bwd")
+                                      ge.data_ptr(), gr.data_ptr(), ws.data_ptr(), ws.numel(), st), "bwd")
         outs.append((ge, gr))
     torch.cuda.synchronize()
     for a, b in zip(outs[0], outs[1]):

@@ -71,8 +71,9 @@ def main():
     out["net_density_ms"] = timeit(lambda: L.ngp_net_forward(C.byref(net), C.byref(smp), 0, sig.data_ptr(), None, None, None, st), flush=flush)
     dsig = torch.randn(n, device=dev) * 1e-3; drgb = torch.randn(n, 3, device=dev) * 1e-2
     ge = torch.zeros_like(model.xyz_encoder.params); gr = torch.zeros_like(model.rgb_net.params)
-    out["net_bwd_ms"] = timeit(lambda: L.ngp_net_backward(C.byref(net), C.byref(smp), dsig.data_ptr(), drgb.data_ptr(), feat.data_ptr(), None, ge.data_ptr(), gr.data_ptr(), None, 0, st), flush=flush)
-    out["net_bwd_regather_ms"] = timeit(lambda: L.ngp_net_backward(C.byref(net), C.byref(smp), dsig.data_ptr(), drgb.data_ptr(), None, None, ge.data_ptr(), gr.data_ptr(), None, 0, st), flush=flush)
+    bws = torch.empty(L.ngp_net_backward_workspace(n), device=dev, dtype=torch.uint8)
+    out["net_bwd_ms"] = timeit(lambda: L.ngp_net_backward(C.byref(net), C.byref(smp), dsig.data_ptr(), drgb.data_ptr(), feat.data_ptr(), None, ge.data_ptr(), gr.data_ptr(), bws.data_ptr(), bws.numel(), st), flush=flush)
+    out["net_bwd_regather_ms"] = timeit(lambda: L.ngp_net_backward(C.byref(net), C.byref(smp), dsig.data_ptr(), drgb.data_ptr(), None, None, ge.data_ptr(), gr.data_ptr(), bws.data_ptr(), bws.numel(), st), flush=flush)
     out["composite_fw_ms"] = timeit(lambda: vren.composite_train_fw(sig, rgb, deltas[:n], ts[:n], rays_a, 1e-4), flush=flush)
     out["cast_params_ms"] = timeit(lambda: L.ngp_cast_params(model.xyz_encoder.params.data_ptr(), keep[0].data_ptr(), model.xyz_encoder.params.numel(), st), flush=flush)
     out["zero_grad_ms"] = timeit(lambda: ge.zero_(), flush=flush)
