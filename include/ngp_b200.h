@@ -161,6 +161,13 @@ int ngp_net_backward(const NgpNet* net, const NgpSamples* smp, const float* dL_d
                      const void* feat_save, const float* loss_scale, float* grad_enc, float* grad_rgb,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* The two halves of ngp_net_backward, individually callable (profiling; overlapping them with other work). */
+int ngp_net_backward_mlp(const NgpNet* net, const NgpSamples* smp, const float* dL_dsigmas, const float* dL_drgbs,
+                         const void* feat_save, const float* loss_scale, float* grad_enc, float* grad_rgb,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int ngp_net_backward_scatter(const NgpNet* net, const NgpSamples* smp, const float* loss_scale, float* grad_enc,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* loss_scale helper: *scale_out = 2^floor(log2(256 / max(|dL_dsigmas*sigma'|, |dL_drgbs|))) (1 if all zero). */
 int ngp_grad_scale(const float* dL_dsigmas, const float* sigmas, const float* dL_drgbs, int64_t n,
                    float* scratch /* 1 float */, float* scale_out, void* stream);

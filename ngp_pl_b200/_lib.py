@@ -124,6 +124,8 @@ SIGNATURES = {
     "ngp_net_forward": (_i, [C.POINTER(NgpNet), C.POINTER(NgpSamples), _i, _P, _P, _P, _P, _P]),
     "ngp_net_backward_workspace": (_sz, [_i64]),
     "ngp_net_backward": (_i, [C.POINTER(NgpNet), C.POINTER(NgpSamples), _P, _P, _P, _P, _P, _P, _P, _sz, _P]),
+    "ngp_net_backward_mlp": (_i, [C.POINTER(NgpNet), C.POINTER(NgpSamples), _P, _P, _P, _P, _P, _P, _P, _sz, _P]),
+    "ngp_net_backward_scatter": (_i, [C.POINTER(NgpNet), C.POINTER(NgpSamples), _P, _P, _P, _sz, _P]),
     "ngp_grad_scale": (_i, [_P, _P, _P, _i64, _P, _P, _P]),
     "ngp_train_scan_temp_bytes": (_sz, [_i]),
     "ngp_render_train_fwd": (_i, [C.POINTER(NgpNet), C.POINTER(NgpTrainCfg), C.POINTER(NgpTrainBuffers), _P]),

@@ -691,34 +691,61 @@ extern "C" size_t ngp_net_backward_workspace(int64_t n) {
     return (size_t)n16 * NGP_MAX_LEVELS * sizeof(uint32_t);
 }
 
-extern "C" int ngp_net_backward(const NgpNet* net, const NgpSamples* smp, const float* dL_dsigmas, const float* dL_drgbs,
-                                const void* feat_save, const float* loss_scale, float* grad_enc, float* grad_rgb,
-                                void* workspace, size_t workspace_bytes, void* stream) {
-    if (!net || !smp || smp->n < 0 || !dL_dsigmas || !dL_drgbs || !grad_enc || !grad_rgb) return NGP_EINVAL;
+static int check_bwd_args(const NgpNet* net, const NgpSamples* smp, void* workspace, size_t workspace_bytes) {
+    if (!net || !smp || smp->n < 0) return NGP_EINVAL;
     if (net->meta.n_levels < 1 || net->meta.n_levels > NGP_MAX_LEVELS) return NGP_EINVAL;
+    if (smp->n > 0 && (!workspace || workspace_bytes < ngp_net_backward_workspace(smp->n))) return NGP_EINVAL;
+    return 0;
+}
+
+// first half: MLP backward (dgrad + wgrad), feature gradients -> workspace
+extern "C" int ngp_net_backward_mlp(const NgpNet* net, const NgpSamples* smp, const float* dL_dsigmas, const float* dL_drgbs,
+                                    const void* feat_save, const float* loss_scale, float* grad_enc, float* grad_rgb,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_bwd_args(net, smp, workspace, workspace_bytes);
+    if (rc) return rc;
+    if (!dL_dsigmas || !dL_drgbs || !grad_enc || !grad_rgb) return NGP_EINVAL;
     if (smp->n == 0) return 0;
-    if (!workspace || workspace_bytes < ngp_net_backward_workspace(smp->n)) return NGP_EINVAL;
     static bool attr_set = false;
     if (!attr_set) {
         NGP_CUDA(cudaFuncSetAttribute(k_ngp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
         attr_set = true;
     }
-    cudaStream_t st = (cudaStream_t)stream;
     const int64_t n_mtiles = (smp->n + 15) / 16;
     const int64_t n_blks = (n_mtiles + BWD_WARPS - 1) / BWD_WARPS;
     const int grid = (int)(n_blks < (int64_t)ngp_sm_count() ? n_blks : ngp_sm_count());
-    const int64_t stride = n_mtiles * 16;
-    k_ngp_bwd<<<grid, BWD_THREADS, sizeof(BwdSmem), st>>>(*net, *smp, dL_dsigmas, dL_drgbs, (const uint4*)feat_save,
-                                                          loss_scale, grad_enc, grad_rgb, (uint32_t*)workspace, stride);
+    k_ngp_bwd<<<grid, BWD_THREADS, sizeof(BwdSmem), (cudaStream_t)stream>>>(
+        *net, *smp, dL_dsigmas, dL_drgbs, (const uint4*)feat_save, loss_scale, grad_enc, grad_rgb, (uint32_t*)workspace,
+        n_mtiles * 16);
     NGP_CHECK_LAUNCH();
+    return 0;
+}
+
+// second half: feature gradients in workspace -> hash-table gradient
+extern "C" int ngp_net_backward_scatter(const NgpNet* net, const NgpSamples* smp, const float* loss_scale, float* grad_enc,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_bwd_args(net, smp, workspace, workspace_bytes);
+    if (rc) return rc;
+    if (!grad_enc) return NGP_EINVAL;
+    if (smp->n == 0) return 0;
+    const int64_t n_mtiles = (smp->n + 15) / 16;
     int64_t gx = (smp->n + SCATTER_THREADS - 1) / SCATTER_THREADS;
     const int64_t cap = (int64_t)ngp_sm_count() * 8 / net->meta.n_levels + 1;
     if (gx > cap) gx = cap;
     dim3 sg((unsigned)gx, (unsigned)net->meta.n_levels);
-    k_grid_scatter_merged<<<sg, SCATTER_THREADS, 0, st>>>(*net, *smp, (const uint32_t*)workspace, stride, loss_scale,
-                                                          grad_enc + NGP_DENSITY_MLP_PARAMS);
+    k_grid_scatter_merged<<<sg, SCATTER_THREADS, 0, (cudaStream_t)stream>>>(
+        *net, *smp, (const uint32_t*)workspace, n_mtiles * 16, loss_scale, grad_enc + NGP_DENSITY_MLP_PARAMS);
     NGP_CHECK_LAUNCH();
     return 0;
+}
+
+extern "C" int ngp_net_backward(const NgpNet* net, const NgpSamples* smp, const float* dL_dsigmas, const float* dL_drgbs,
+                                const void* feat_save, const float* loss_scale, float* grad_enc, float* grad_rgb,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = ngp_net_backward_mlp(net, smp, dL_dsigmas, dL_drgbs, feat_save, loss_scale, grad_enc, grad_rgb, workspace,
+                                  workspace_bytes, stream);
+    if (rc) return rc;
+    return ngp_net_backward_scatter(net, smp, loss_scale, grad_enc, workspace, workspace_bytes, stream);
 }
 
 // -------------------------------------------------------------------------------------------------
