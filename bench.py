@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--fps-views", type=int, default=5)
     ap.add_argument("--no-fps", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ddp", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1 gradient exchange: fused NVLink reduce-scatter+Adam+all-gather kernel, or NCCL all-reduce")
     return ap.parse_args()
 
 
@@ -197,7 +199,15 @@ def run_b200(args):
     scene = synth.lego_scene(0)
     bank = synth.RayBank(scene, n_images=N_TRAIN_IMAGES, device=dev, seed=rank)  # every rank: own images order/sampling
     model = NGP(scene.scale).to(dev)
-    tr = Trainer(model, n_rays=N_RAYS, lr=1e-2, process_group=pg, world_size=world, rank=rank, seed=rank)
+    ddp_mode = args.ddp
+    try:
+        tr = Trainer(model, n_rays=N_RAYS, lr=1e-2, process_group=pg, world_size=world, rank=rank, seed=rank, ddp=ddp_mode)
+    except Exception as e:  # symmetric memory unavailable: fall back to NCCL and say so in the line
+        if world == 1 or ddp_mode == "nccl":
+            raise
+        ddp_mode = "nccl (p2p unavailable: %s)" % type(e).__name__
+        model = NGP(scene.scale).to(dev)
+        tr = Trainer(model, n_rays=N_RAYS, lr=1e-2, process_group=pg, world_size=world, rank=rank, seed=rank, ddp="nccl")
     tr.attach_bank(bank)
     pretrain = args.pretrain if args.pretrain is not None else 1000
     K, W = args.steps, max(args.warmup, 3)
@@ -332,7 +342,9 @@ def run_b200(args):
                 "pre-trained %d untimed steps)" % pretrain,
         "config": {"workload": "BASELINE config 2: Lego 800x800, 8192 rays/step/GPU, L=16 T=2^19 F=2, Adam lr 1e-2, "
                                "occupancy refresh every 16 steps", "rays_per_step_per_gpu": N_RAYS, "global_rays_per_step": world * N_RAYS,
-                   "parallelism": "dp%d" % world, "pretrain_steps": pretrain,
+                   "parallelism": "dp%d" % world + ("" if world == 1 else " [%s]" % (
+                       "fused NVLink reduce-scatter+Adam+all-gather kernel" if ddp_mode == "p2p" else ddp_mode)),
+                   "pretrain_steps": pretrain,
                    "l2": "no explicit flush: each step streams params+grads+Adam moments (~230 MB) > 126 MB L2",
                    "samples_per_ray_marched": stats["rm_samples"] / N_RAYS, "samples_per_ray_composited": stats["vr_samples"] / N_RAYS,
                    "train_psnr_last_batch": stats["psnr"]},
@@ -367,15 +379,19 @@ def make_ddp_step(tr, sample=True):
             tr.sample_batch()
         tr.forward()
         tr.loss_backward()
-    with torch.cuda.graph(g2):
-        tr.optimizer_step()
+    if tr.ddp != "p2p":
+        with torch.cuda.graph(g2):
+            tr.optimizer_step()
 
     def step():
         if tr.host_step % tr.update_interval == 0:
             tr.update_density_grid(warmup=tr.host_step < tr.warmup_steps)
         g1.replay()
-        tr.allreduce()
-        g2.replay()
+        if tr.ddp == "p2p":
+            tr.optimizer_step()  # barrier, fused NVLink kernel, barrier, clear gradients
+        else:
+            tr.allreduce()
+            g2.replay()
         tr.host_step += 1
     return step
 
@@ -501,3 +517,9 @@ if __name__ == "__main__":
         run_reference(a)
     else:
         run_b200(a)
+    try:
+        import torch.distributed as _d
+        if _d.is_initialized():
+            _d.destroy_process_group()
+    except Exception:
+        pass

@@ -246,6 +246,17 @@ int ngp_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq
                   const float* lr_dev, int32_t* step_dev, float beta1, float beta2, float eps, float grad_mul,
                   int increment_step, void* stream);
 
+/* Data-parallel optimiser step FUSED with its collective over NVLink peer memory (N ranks of one node):
+ * rank `rank` reduces its 1/N shard of the gradient directly from every rank's gradient buffer (P2P loads),
+ * applies Adam (mean gradient, same semantics as ngp_adam_step) to that shard of params / exp_avg /
+ * exp_avg_sq, and stores the shard's new fp16 parameters into every rank's working copy (P2P stores).
+ * peer_grads / peer_params_half: HOST arrays of `world` device addresses valid on this rank (symmetric
+ * memory; index = rank). The caller must barrier across ranks before (all gradients written) and after
+ * (all parameter stores visible), then clear its own gradient buffer. n must be a multiple of 4. */
+int ngp_adam_step_p2p(int world, int rank, const uint64_t* peer_grads, float* params, float* exp_avg, float* exp_avg_sq,
+                      const uint64_t* peer_params_half, int64_t n, const float* lr_dev, int32_t* step_dev, float beta1,
+                      float beta2, float eps, int increment_step, void* stream);
+
 /* Batch assembly on the device (reference train.py:78-91 + datasets/ray_utils.py:46-70 + base.py:22-30):
  * rays_d = directions[pix] @ R^T, rays_o = c2w[:,3], rgb_gt = images[img, pix] / 255. */
 int ngp_gen_rays(const int64_t* img_idx, const int64_t* pix_idx, const float* poses /* (n_img,3,4) */,

@@ -352,6 +352,97 @@ extern "C" int ngp_adam_step(float* params, float* grads, float* exp_avg, float*
 }
 
 // -------------------------------------------------------------------------------------------------
+// Data-parallel optimiser step fused with its collective over NVLink peer memory (one kernel):
+//   reduce-scatter : rank r sums ITS 1/N shard of the gradient straight out of every peer's gradient
+//                    buffer (128-bit P2P loads over NVLink / NVSwitch; no staging copy, no NCCL),
+//   Adam           : on that shard only (optimiser state and its HBM traffic are sharded N ways),
+//   all-gather     : the updated fp16 parameters of the shard are stored into EVERY peer's working copy.
+// Replaces all_reduce(45.8 MB) + a full-size Adam pass. The caller brackets it with two cross-GPU
+// barriers (all gradients complete before; all parameter stores landed after) and clears its own
+// gradient buffer afterwards. The fp32 master copy of a shard lives on its owner only.
+// -------------------------------------------------------------------------------------------------
+#define NGP_MAX_PEERS 16
+struct PeerPtrs {
+    const float* grads[NGP_MAX_PEERS];
+    __half* params_half[NGP_MAX_PEERS];
+};
+
+__global__ void k_adam_p2p(const PeerPtrs peers, const int world, float* __restrict__ p, float* __restrict__ m,
+                           float* __restrict__ v, const int64_t lo4, const int64_t hi4, const float* __restrict__ lr_dev,
+                           const int* __restrict__ step_dev, float beta1, float beta2, float eps, float grad_mul) {
+    const int t = *step_dev + 1;
+    const float lr = *lr_dev;
+    const float bc1 = 1.0f - powf(beta1, (float)t);
+    const float bc2 = 1.0f - powf(beta2, (float)t);
+    const float step_size = lr / bc1;
+    const float inv_sqrt_bc2 = rsqrtf(bc2);
+    for (int64_t i = lo4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < hi4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 part[NGP_MAX_PEERS];
+#pragma unroll
+        for (int r = 0; r < NGP_MAX_PEERS; ++r)
+            if (r < world) part[r] = __ldcg(reinterpret_cast<const float4*>(peers.grads[r]) + i);  // all loads in flight
+#pragma unroll
+        for (int r = 0; r < NGP_MAX_PEERS; ++r)
+            if (r < world) { g.x += part[r].x; g.y += part[r].y; g.z += part[r].z; g.w += part[r].w; }
+        float4 pv = reinterpret_cast<float4*>(p)[i];
+        float4 mv = reinterpret_cast<float4*>(m)[i];
+        float4 vv = reinterpret_cast<float4*>(v)[i];
+        float* pp = &pv.x; float* gp = &g.x; float* mp = &mv.x; float* vp = &vv.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gr = gp[k] * grad_mul;
+            mp[k] = beta1 * mp[k] + (1.0f - beta1) * gr;
+            vp[k] = beta2 * vp[k] + (1.0f - beta2) * gr * gr;
+            pp[k] -= step_size * (mp[k] / (sqrtf(vp[k]) * inv_sqrt_bc2 + eps));
+        }
+        reinterpret_cast<float4*>(p)[i] = pv;
+        reinterpret_cast<float4*>(m)[i] = mv;
+        reinterpret_cast<float4*>(v)[i] = vv;
+        uint2 h;
+        h.x = pack_half2(pv.x, pv.y);
+        h.y = pack_half2(pv.z, pv.w);
+#pragma unroll
+        for (int r = 0; r < NGP_MAX_PEERS; ++r)
+            if (r < world) reinterpret_cast<uint2*>(peers.params_half[r])[i] = h;
+    }
+}
+
+extern "C" int ngp_adam_step_p2p(int world, int rank, const uint64_t* peer_grads, float* params, float* exp_avg,
+                                 float* exp_avg_sq, const uint64_t* peer_params_half, int64_t n, const float* lr_dev,
+                                 int32_t* step_dev, float beta1, float beta2, float eps, int increment_step, void* stream) {
+    if (world < 1 || world > NGP_MAX_PEERS || rank < 0 || rank >= world || !peer_grads || !peer_params_half || !params ||
+        !exp_avg || !exp_avg_sq || !lr_dev || !step_dev || n < 0 || (n & 3))
+        return NGP_EINVAL;
+    PeerPtrs pp;
+    for (int r = 0; r < NGP_MAX_PEERS; ++r) {
+        pp.grads[r] = r < world ? (const float*)(uintptr_t)peer_grads[r] : nullptr;
+        pp.params_half[r] = r < world ? (__half*)(uintptr_t)peer_params_half[r] : nullptr;
+        if (r < world && (((uintptr_t)pp.grads[r] & 15) || ((uintptr_t)pp.params_half[r] & 7))) return NGP_EINVAL;
+    }
+    if (((uintptr_t)params | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) return NGP_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    // contiguous shard of float4 elements owned by this rank
+    const int64_t n4 = n >> 2;
+    const int64_t base = n4 / world, extra = n4 % world;
+    const int64_t lo4 = rank * base + (rank < extra ? rank : extra);
+    const int64_t hi4 = lo4 + base + (rank < extra ? 1 : 0);
+    if (hi4 > lo4) {
+        int grid = ngp_div_up(hi4 - lo4, 256);
+        const int cap = ngp_sm_count() * 8;
+        if (grid > cap) grid = cap;
+        k_adam_p2p<<<grid, 256, 0, st>>>(pp, world, params, exp_avg, exp_avg_sq, lo4, hi4, lr_dev, step_dev, beta1, beta2,
+                                          eps, 1.0f / (float)world);
+        NGP_CHECK_LAUNCH();
+    }
+    if (increment_step) {
+        k_step_inc<<<1, 1, 0, st>>>(step_dev);
+        NGP_CHECK_LAUNCH();
+    }
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
 // batch assembly (reference train.py:78-91, datasets/ray_utils.py:46-70)
 // -------------------------------------------------------------------------------------------------
 __global__ void k_gen_rays(const int64_t* __restrict__ img_idx, const int64_t* __restrict__ pix_idx,

@@ -51,7 +51,7 @@ def shard_range(n_items, world_size, rank):
 class Trainer:
     def __init__(self, model: NGP, n_rays=8192, lr=1e-2, exp_step_factor=0.0, bg=(1.0, 1.0, 1.0), lambda_opacity=1e-3,
                  T_threshold=1e-4, betas=(0.9, 0.999), eps=1e-15, max_total_samples=None, update_interval=16,
-                 warmup_steps=256, process_group=None, world_size=1, rank=0, seed=0, materialize_ws=False):
+                 warmup_steps=256, process_group=None, world_size=1, rank=0, seed=0, materialize_ws=False, ddp="nccl"):
         self.model = model
         dev = model.density_bitfield.device
         if dev.type != "cuda":
@@ -65,6 +65,9 @@ class Trainer:
         self.exp_step_factor = float(exp_step_factor)
         self.host_step = 0
         self.seed = seed
+        # "nccl": all_reduce of the flat gradient + full Adam on every rank;
+        # "p2p" : ngp_adam_step_p2p (reduce-scatter + sharded Adam + all-gather in ONE kernel over NVLink peer memory)
+        self.ddp = ddp if self.world_size > 1 else "none"
         L = _lib.lib()
 
         # ---- flat parameter / gradient / optimiser state --------------------------------------------------
@@ -78,10 +81,23 @@ class Trainer:
             self.P[self.n_enc:].copy_(pr.data)
             pe.data = self.P[:self.n_enc]
             pr.data = self.P[self.n_enc:]
-            self.G = torch.zeros(n, device=dev, dtype=torch.float32)
+            if self.ddp == "p2p":
+                # gradient buffer and fp16 working copy live in symmetric (peer-mapped) memory
+                import torch.distributed as dist
+                import torch.distributed._symmetric_memory as symm_mem
+                grp = self.pg if self.pg is not None else dist.group.WORLD
+                self.G = symm_mem.empty(n, dtype=torch.float32, device=dev)
+                self.G.zero_()
+                self.Ph = symm_mem.empty(n, dtype=torch.float16, device=dev)
+                self.hG = symm_mem.rendezvous(self.G, grp)
+                self.hPh = symm_mem.rendezvous(self.Ph, grp)
+                self.peer_G = (C.c_uint64 * self.world_size)(*[int(p) for p in self.hG.buffer_ptrs])
+                self.peer_Ph = (C.c_uint64 * self.world_size)(*[int(p) for p in self.hPh.buffer_ptrs])
+            else:
+                self.G = torch.zeros(n, device=dev, dtype=torch.float32)
+                self.Ph = torch.empty(n, device=dev, dtype=torch.float16)
             self.M = torch.zeros(n, device=dev, dtype=torch.float32)
             self.V = torch.zeros(n, device=dev, dtype=torch.float32)
-            self.Ph = torch.empty(n, device=dev, dtype=torch.float16)
             _lib.check(L.ngp_cast_params(self.P.data_ptr(), self.Ph.data_ptr(), n, self._st()), "cast_params")
             # the module-level API (NGP.forward / density / render) must see the weights this trainer updates
             from .tcnn import _FixedHalf
@@ -231,13 +247,42 @@ class Trainer:
                                           self.G[self.n_enc:].data_ptr(), self._st()), "render_train_bwd")
 
     def allreduce(self):
-        allreduce_gradients(self.G, self.world_size, self.pg)
+        if self.ddp == "nccl":
+            allreduce_gradients(self.G, self.world_size, self.pg)
 
     def optimizer_step(self):
+        if self.ddp == "p2p":
+            return self._optimizer_step_p2p()
         rc = _lib.lib().ngp_adam_step(self.P.data_ptr(), self.G.data_ptr(), self.M.data_ptr(), self.V.data_ptr(),
                                       self.Ph.data_ptr(), self.n_params, self.lr_dev.data_ptr(), self.step_dev.data_ptr(),
                                       self.betas[0], self.betas[1], self.eps, 1.0 / self.world_size, 1, self._st())
         _lib.check(rc, "adam_step")
+
+    def _optimizer_step_p2p(self):
+        """barrier -> fused reduce-scatter + sharded Adam + all-gather over NVLink -> barrier -> clear own gradients"""
+        self.hG.barrier(channel=0)
+        rc = _lib.lib().ngp_adam_step_p2p(self.world_size, self.rank, self.peer_G, self.P.data_ptr(), self.M.data_ptr(),
+                                          self.V.data_ptr(), self.peer_Ph, self.n_params, self.lr_dev.data_ptr(),
+                                          self.step_dev.data_ptr(), self.betas[0], self.betas[1], self.eps, 1, self._st())
+        _lib.check(rc, "adam_step_p2p")
+        self.hG.barrier(channel=0)
+        self.G.zero_()
+
+    def shard_bounds(self, rank=None):
+        """[lo, hi) element range of the parameters whose fp32 master / Adam state `rank` owns in p2p mode"""
+        r = self.rank if rank is None else rank
+        lo4, hi4 = shard_range(self.n_params // 4, self.world_size, r)
+        return 4 * lo4, 4 * hi4
+
+    def gather_master_params(self):
+        """p2p mode keeps the fp32 master copy of each shard on its owner only: broadcast every shard so that
+        state_dict() / checkpoints are complete on every rank (call before saving; synchronises)."""
+        if self.ddp != "p2p":
+            return
+        import torch.distributed as dist
+        for r in range(self.world_size):
+            lo, hi = self.shard_bounds(r)
+            dist.broadcast(self.P[lo:hi], src=r, group=self.pg)
 
     def _step_body(self, sample):
         if sample:

@@ -249,3 +249,19 @@ def test_warp_marcher_bit_exact_vs_oracle(name, oracle):
     assert (tr.ts[:tot].cpu().numpy().view(np.uint32) == ts.view(np.uint32)).all()
     assert (tr.deltas[:tot].cpu().numpy().view(np.uint32) == deltas.view(np.uint32)).all()
     assert (tr.ray_idx[:tot].cpu().numpy() == np.repeat(np.arange(n), ra[:, 2])).all()
+
+
+def test_fused_nvlink_optimizer_step_two_gpus(tmp_path):
+    """ngp_adam_step_p2p (reduce-scatter + sharded Adam + all-gather over NVLink peer memory) == NCCL all-reduce +
+    full Adam, bitwise at N=2 (tools/check_p2p.py under torchrun). Needs two GPUs; skipped on a 1-GPU box."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(root, "tools", "check_p2p.py")],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "MISMATCH" not in r.stdout
