@@ -149,3 +149,43 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, co
     const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_row);
     asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];\n" : "=r"(r0), "=r"(r1) : "r"(a));
 }
+
+// ---- pieces of the layer-sequential backward (k_ngp_bwd2) -------------------------------------------
+
+// dX[16 x N] = dY[16 x K] * W[K rows (out)][N cols (in)]  with W row-major (LD halfs per row) in shared
+// memory: the B fragments (k = out row, n = in column) are the TRANSPOSE of what a plain 32-bit load of
+// W gives, so they are fetched with ldmatrix.trans (two n-tiles per x4), no transposed weight copy needed.
+template <int K, int N, int LD>
+__device__ __forceinline__ void mlp_layer_dgrad(const uint32_t (&A)[1][K / 16][4], const __half* __restrict__ W,
+                                                float (&C)[1][N / 8][4], int lane) {
+#pragma unroll
+    for (int j = 0; j < N / 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) C[0][j][e] = 0.f;
+    const int row = (lane & 7) + 8 * ((lane >> 3) & 1);
+    const int col = 8 * (lane >> 4);
+#pragma unroll
+    for (int kt = 0; kt < K / 16; ++kt) {
+#pragma unroll
+        for (int j = 0; j < N / 8; j += 2) {
+            uint32_t b[4];
+            ldmatrix_x4_trans(b, W + (16 * kt + row) * LD + 8 * j + col);
+            mma_16816(C[0][j], A[0][kt], b[0], b[1]);
+            mma_16816(C[0][j + 1], A[0][kt], b[2], b[3]);
+        }
+    }
+}
+
+// A fragments of 16 rows read back from a [row][channel] shared-memory tile (inverse of stage_frag)
+template <int KT>
+__device__ __forceinline__ void load_frag(const __half* __restrict__ src, int ld, int row0, uint32_t (&A)[1][KT][4], int g, int q) {
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+        const uint32_t* r0 = reinterpret_cast<const uint32_t*>(src + (row0 + g) * ld + 16 * kt + 2 * q);
+        const uint32_t* r1 = reinterpret_cast<const uint32_t*>(src + (row0 + g + 8) * ld + 16 * kt + 2 * q);
+        A[0][kt][0] = r0[0];
+        A[0][kt][1] = r1[0];
+        A[0][kt][2] = r0[4];
+        A[0][kt][3] = r1[4];
+    }
+}

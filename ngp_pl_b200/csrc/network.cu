@@ -612,6 +612,272 @@ k_ngp_bwd(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_d
 }
 
 // -------------------------------------------------------------------------------------------------
+// backward, layer-sequential variant (default): 16 warps per CTA instead of 8, <= 128 registers.
+// The recomputed activations are staged to shared memory as they are produced (they are the `In`
+// operands of the weight-gradient GEMMs anyway) instead of being held in registers until the end; one
+// out-gradient buffer is reused layer after layer:   stage dOut -> sync -> {wgrad tiles of this layer
+// (every warp reads all 256 staged rows), dgrad of this layer (own rows, B fragments by ldmatrix.trans from
+// the forward weights)} -> sync -> next layer.   80 wgrad tiles / 16 warps = 5 accumulator tiles per warp.
+// -------------------------------------------------------------------------------------------------
+#define B2_WARPS 16
+#define B2_THREADS (B2_WARPS * 32)
+#define B2_ROWS (B2_WARPS * 16)
+struct Bwd2Smem {
+    MlpWeightsFwd wf;
+    __half feat[B2_ROWS * LD32];
+    __half hid[B2_ROWS * LD64];
+    __half rin[B2_ROWS * LD32];
+    __half r1[B2_ROWS * LD64];
+    __half r2[B2_ROWS * LD64];
+    __half dout[B2_ROWS * LD64];  // out-gradient of the layer being processed
+};
+
+// one 16x8 tile of dW accumulated over the B2_ROWS staged samples
+__device__ __forceinline__ void wgrad_tile2(float (&acc)[4], const __half* __restrict__ dOut, int ld_o, int mt,
+                                            const __half* __restrict__ In, int ld_i, int nt, int lane) {
+    const int ra = (lane & 7) + 8 * ((lane >> 4) & 1);
+    const int ca = 16 * mt + 8 * ((lane >> 3) & 1);
+    const int rb = (lane & 7) + 8 * ((lane >> 3) & 1);
+    const int cb = 8 * nt;
+#pragma unroll 4
+    for (int ks = 0; ks < B2_ROWS / 16; ++ks) {
+        uint32_t a[4], b0, b1;
+        ldmatrix_x4_trans(a, dOut + (16 * ks + ra) * ld_o + ca);
+        ldmatrix_x2_trans(b0, b1, In + (16 * ks + rb) * ld_i + cb);
+        mma_16816(acc, a, b0, b1);
+    }
+}
+// two tiles sharing the dOut operand (same out-tile, neighbouring in-tiles)
+__device__ __forceinline__ void wgrad_tile2x2(float (&acc0)[4], float (&acc1)[4], const __half* __restrict__ dOut, int ld_o,
+                                              int mt, const __half* __restrict__ In, int ld_i, int nt, int lane) {
+    const int ra = (lane & 7) + 8 * ((lane >> 4) & 1);
+    const int ca = 16 * mt + 8 * ((lane >> 3) & 1);
+    const int rb = (lane & 7) + 8 * ((lane >> 3) & 1);
+    const int cb = 8 * nt + 8 * (lane >> 4);
+#pragma unroll 4
+    for (int ks = 0; ks < B2_ROWS / 16; ++ks) {
+        uint32_t a[4], b[4];
+        ldmatrix_x4_trans(a, dOut + (16 * ks + ra) * ld_o + ca);
+        ldmatrix_x4_trans(b, In + (16 * ks + rb) * ld_i + cb);
+        mma_16816(acc0, a, b[0], b[1]);
+        mma_16816(acc1, a, b[2], b[3]);
+    }
+}
+
+__global__ void __launch_bounds__(B2_THREADS, 1)
+k_ngp_bwd2(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_dsigmas, const float* __restrict__ dL_drgbs,
+           const uint4* __restrict__ feat_save, const float* __restrict__ loss_scale, float* __restrict__ grad_enc,
+           float* __restrict__ grad_rgb, uint32_t* __restrict__ dfeat, const int64_t dfeat_stride) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Bwd2Smem& S = *reinterpret_cast<Bwd2Smem*>(smem_raw);
+    const __half* wd = reinterpret_cast<const __half*>(net.enc_params_h);
+    const __half* wr = reinterpret_cast<const __half*>(net.rgb_params_h);
+    load_weights_fwd(S.wf, wd, wr, threadIdx.x, B2_THREADS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    const int64_t n = sample_count(smp);
+    const int64_t n_mtiles = (n + 15) / 16;
+    const int64_t n_blks = (n_mtiles + B2_WARPS - 1) / B2_WARPS;
+    const float scale = loss_scale ? *loss_scale : 1.0f;
+    const float inv_scale = 1.0f / scale;
+    const int row0 = 16 * warp;
+    const int wm = warp >> 2, wn = warp & 3;  // (out-tile, in-tile) role of this warp in the 16-tile GEMMs
+
+    // accumulators: [0] W3r (warps 0-7) or W2d (warps 8-15), [1],[2] W2r, [3] W1r, [4] W1d
+    float acc[5][4];
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+
+    for (int64_t blk = blockIdx.x; blk < n_blks; blk += gridDim.x) {
+        const int64_t mtile = blk * B2_WARPS + warp;
+        const int64_t base = mtile * 16;
+        bool valid[2];
+        float up_sig[2] = {0.f, 0.f}, up_c0[2] = {0.f, 0.f}, up_c1[2] = {0.f, 0.f};
+        SampleIn sm[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t row = base + g + 8 * h;
+            valid[h] = row < n;
+            sm[h] = load_sample(smp, row, valid[h]);
+            if (valid[h]) {
+                if (q == 0) {
+                    up_sig[h] = __ldg(dL_dsigmas + row);
+                    up_c0[h] = __ldg(dL_drgbs + 3 * row);
+                    up_c1[h] = __ldg(dL_drgbs + 3 * row + 1);
+                } else if (q == 1) {
+                    up_c0[h] = __ldg(dL_drgbs + 3 * row + 2);
+                }
+            }
+        }
+        uint32_t featA[1][2][4];
+        if (base < n) {
+#pragma unroll
+            for (int kt = 0; kt < 2; ++kt) {
+                const uint4 v = __ldg(feat_save + (mtile * 2 + kt) * 32 + lane);
+                featA[0][kt][0] = v.x; featA[0][kt][1] = v.y; featA[0][kt][2] = v.z; featA[0][kt][3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int kt = 0; kt < 2; ++kt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) featA[0][kt][e] = 0u;
+        }
+        // every warp is done with the previous iteration's staged tensors (and, first time, the weights are loaded)
+        __syncthreads();
+
+        // ---- forward recompute, staging each activation as soon as it exists ----
+        stage_frag<2>(S.feat, LD32, row0, featA[0], g, q);
+        float h0[2];
+        uint32_t hA[1][1][4];
+        {
+            uint32_t hidA[1][4][4];
+            {
+                float c[1][8][4];
+                mlp_layer<1, 32, 64, LD32>(featA, S.wf.w1d, c, g, q);
+                relu_to_frag<1, 64>(c, hidA);
+            }
+            stage_frag<4>(S.hid, LD64, row0, hidA[0], g, q);
+            float c[1][2][4];
+            mlp_layer<1, 64, 16, LD64>(hidA, S.wf.w2d, c, g, q);
+            to_frag<1, 16>(c, hA);
+        }
+        h0[0] = lo_half(hA[0][0][0]);
+        h0[1] = lo_half(hA[0][0][1]);
+        uint32_t doutA[1][1][4];
+        {
+            uint32_t inA[1][2][4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) sh_rows(sm[h], q, inA[0][0][h], inA[0][0][2 + h]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) inA[0][1][e] = hA[0][0][e];
+            stage_frag<2>(S.rin, LD32, row0, inA[0], g, q);
+            uint32_t r1A[1][4][4];
+            {
+                float c[1][8][4];
+                mlp_layer<1, 32, 64, LD32>(inA, S.wf.w1r, c, g, q);
+                relu_to_frag<1, 64>(c, r1A);
+            }
+            stage_frag<4>(S.r1, LD64, row0, r1A[0], g, q);
+            uint32_t r2A[1][4][4];
+            {
+                float c[1][8][4];
+                mlp_layer<1, 64, 64, LD64>(r1A, S.wf.w2r, c, g, q);
+                relu_to_frag<1, 64>(c, r2A);
+            }
+            stage_frag<4>(S.r2, LD64, row0, r2A[0], g, q);
+            float oC[1][1][4];
+            mlp_layer<1, 64, 8, LD64>(r2A, S.wf.w3r, oC, g, q);
+            doutA[0][0][2] = 0u;
+            doutA[0][0][3] = 0u;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float d0 = 0.f, d1 = 0.f;
+                if (valid[h] && q < 2) {
+                    float o0 = oC[0][0][2 * h], o1 = oC[0][0][2 * h + 1];
+                    float s0 = 1.f, s1 = 1.f;
+                    if (net.rgb_act == 1) {
+                        o0 = half_round(1.0f / (1.0f + __expf(-o0)));
+                        o1 = half_round(1.0f / (1.0f + __expf(-o1)));
+                        s0 = o0 * (1.0f - o0);
+                        s1 = o1 * (1.0f - o1);
+                    }
+                    d0 = up_c0[h] * s0 * scale;
+                    d1 = (q == 0) ? up_c1[h] * s1 * scale : 0.f;
+                }
+                doutA[0][0][h] = pack_half2(d0, d1);
+            }
+        }
+
+        // ---- layer rgb-3 : W3r (16 x 64) ----
+        stage_frag<1>(S.dout, LD64, row0, doutA[0], g, q);
+        __syncthreads();
+        if (warp < 8) wgrad_tile2(acc[0], S.dout, LD64, 0, S.r2, LD64, warp, lane);
+        uint32_t dA[1][4][4];  // out-gradient fragments of the 64-wide layers, reused
+        {
+            float c[1][8][4];
+            mlp_layer_dgrad<16, 64, LD64>(doutA, S.wf.w3r, c, lane);
+            uint32_t act[1][4][4];
+            load_frag<4>(S.r2, LD64, row0, act, g, q);
+            relu_bwd_to_frag<1, 64>(c, act, dA);
+        }
+        __syncthreads();
+
+        // ---- layer rgb-2 : W2r (64 x 64) ----
+        stage_frag<4>(S.dout, LD64, row0, dA[0], g, q);
+        __syncthreads();
+        wgrad_tile2x2(acc[1], acc[2], S.dout, LD64, wm, S.r1, LD64, 2 * wn, lane);
+        {
+            float c[1][8][4];
+            mlp_layer_dgrad<64, 64, LD64>(dA, S.wf.w2r, c, lane);
+            uint32_t act[1][4][4];
+            load_frag<4>(S.r1, LD64, row0, act, g, q);
+            relu_bwd_to_frag<1, 64>(c, act, dA);
+        }
+        __syncthreads();
+
+        // ---- layer rgb-1 : W1r (64 x 32); only the h half of its input needs a gradient ----
+        stage_frag<4>(S.dout, LD64, row0, dA[0], g, q);
+        __syncthreads();
+        wgrad_tile2(acc[3], S.dout, LD64, wm, S.rin, LD32, wn, lane);
+        uint32_t dhA[1][1][4];
+        {
+            float c[1][2][4];
+            mlp_layer_dgrad<64, 16, LD32>(dA, S.wf.w1r + 16, c, lane);
+            if (q == 0) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    if (valid[h]) c[0][0][2 * h] += up_sig[h] * expf(fminf(fmaxf(h0[h], -15.f), 15.f)) * scale;
+            }
+            to_frag<1, 16>(c, dhA);
+        }
+        __syncthreads();
+
+        // ---- layer density-2 : W2d (16 x 64) ----
+        stage_frag<1>(S.dout, LD64, row0, dhA[0], g, q);
+        __syncthreads();
+        if (warp >= 8) wgrad_tile2(acc[0], S.dout, LD64, 0, S.hid, LD64, warp - 8, lane);
+        {
+            float c[1][8][4];
+            mlp_layer_dgrad<16, 64, LD64>(dhA, S.wf.w2d, c, lane);
+            uint32_t act[1][4][4];
+            load_frag<4>(S.hid, LD64, row0, act, g, q);
+            relu_bwd_to_frag<1, 64>(c, act, dA);
+        }
+        __syncthreads();
+
+        // ---- layer density-1 : W1d (64 x 32) -> feature gradients ----
+        stage_frag<4>(S.dout, LD64, row0, dA[0], g, q);
+        __syncthreads();
+        wgrad_tile2(acc[4], S.dout, LD64, wm, S.feat, LD32, wn, lane);
+        {
+            float c[1][4][4];
+            mlp_layer_dgrad<64, 32, LD32>(dA, S.wf.w1d, c, lane);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int64_t row = base + g + 8 * h;
+                if (!valid[h]) continue;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int level = 4 * j + q;
+                    if (level < net.meta.n_levels)
+                        dfeat[(int64_t)level * dfeat_stride + row] = pack_half2(c[0][j][2 * h], c[0][j][2 * h + 1]);
+                }
+            }
+        }
+    }
+
+    // ---- flush the weight-gradient tiles ----
+    if (warp < 8) wgrad_flush(acc[0], grad_rgb + 2048 + 4096, 64, 0, warp, inv_scale, g, q);  // W3r
+    else wgrad_flush(acc[0], grad_enc + 2048, 64, 0, warp - 8, inv_scale, g, q);              // W2d
+    wgrad_flush(acc[1], grad_rgb + 2048, 64, wm, 2 * wn, inv_scale, g, q);                    // W2r
+    wgrad_flush(acc[2], grad_rgb + 2048, 64, wm, 2 * wn + 1, inv_scale, g, q);
+    wgrad_flush(acc[3], grad_rgb, 32, wm, wn, inv_scale, g, q);                               // W1r
+    wgrad_flush(acc[4], grad_enc, 32, wm, wn, inv_scale, g, q);                               // W1d
+}
+
+// -------------------------------------------------------------------------------------------------
 // hash-table gradient scatter: one thread per (sample, level), a warp = 32 CONSECUTIVE samples of one
 // level. Consecutive samples of a ray fall into the same cell at the coarse levels, so equal cells are
 // contiguous lane runs: their 16 corner contributions are summed with a segmented shuffle reduction and
@@ -709,14 +975,28 @@ extern "C" int ngp_net_backward_mlp(const NgpNet* net, const NgpSamples* smp, co
     static bool attr_set = false;
     if (!attr_set) {
         NGP_CUDA(cudaFuncSetAttribute(k_ngp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
+        NGP_CUDA(cudaFuncSetAttribute(k_ngp_bwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Bwd2Smem)));
         attr_set = true;
     }
+    static int variant = -1;  // NGP_BWD_VARIANT=0 selects the 8-warp all-at-once kernel (also used when re-gathering)
+    if (variant < 0) {
+        const char* e = getenv("NGP_BWD_VARIANT");
+        variant = e ? atoi(e) : 1;
+    }
     const int64_t n_mtiles = (smp->n + 15) / 16;
-    const int64_t n_blks = (n_mtiles + BWD_WARPS - 1) / BWD_WARPS;
-    const int grid = (int)(n_blks < (int64_t)ngp_sm_count() ? n_blks : ngp_sm_count());
-    k_ngp_bwd<<<grid, BWD_THREADS, sizeof(BwdSmem), (cudaStream_t)stream>>>(
-        *net, *smp, dL_dsigmas, dL_drgbs, (const uint4*)feat_save, loss_scale, grad_enc, grad_rgb, (uint32_t*)workspace,
-        n_mtiles * 16);
+    if (variant == 0 || !feat_save) {
+        const int64_t n_blks = (n_mtiles + BWD_WARPS - 1) / BWD_WARPS;
+        const int grid = (int)(n_blks < (int64_t)ngp_sm_count() ? n_blks : ngp_sm_count());
+        k_ngp_bwd<<<grid, BWD_THREADS, sizeof(BwdSmem), (cudaStream_t)stream>>>(
+            *net, *smp, dL_dsigmas, dL_drgbs, (const uint4*)feat_save, loss_scale, grad_enc, grad_rgb, (uint32_t*)workspace,
+            n_mtiles * 16);
+    } else {
+        const int64_t n_blks = (n_mtiles + B2_WARPS - 1) / B2_WARPS;
+        const int grid = (int)(n_blks < (int64_t)ngp_sm_count() ? n_blks : ngp_sm_count());
+        k_ngp_bwd2<<<grid, B2_THREADS, sizeof(Bwd2Smem), (cudaStream_t)stream>>>(
+            *net, *smp, dL_dsigmas, dL_drgbs, (const uint4*)feat_save, loss_scale, grad_enc, grad_rgb, (uint32_t*)workspace,
+            n_mtiles * 16);
+    }
     NGP_CHECK_LAUNCH();
     return 0;
 }
