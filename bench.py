@@ -214,12 +214,10 @@ def run_b200(args):
     sampler = ClockSampler(local)
     sampler.start()
 
-    # graphs: single GPU = one graph per step; multi GPU = [fwd+bwd] graph, eager NCCL all-reduce, [Adam] graph
-    if world == 1:
-        tr.capture(sample=True)
-        step = tr.train_step
-    else:
-        step = make_ddp_step(tr)
+    # CUDA graphs: [batch + march] / [network fwd + loss + bwd] / [Adam]; the next step's [batch + march] replays on
+    # a side stream while this step's optimiser (Adam, or all-reduce / the fused NVLink kernel for N>1) runs
+    tr.capture(sample=True)
+    step = tr.train_step
     for _ in range(pretrain):
         step()
     for _ in range(W):
@@ -244,11 +242,8 @@ def run_b200(args):
     n_host = 32
     host = [tuple(t.cpu().pin_memory() for t in bank.sample(N_RAYS)) for _ in range(n_host)]
     out_host = torch.zeros(8, dtype=torch.float32).pin_memory()
-    if world == 1:
-        tr.capture(sample=False)
-        step_nosample = lambda: tr.train_step(sample=False)
-    else:
-        step_nosample = make_ddp_step(tr, sample=False)
+    tr.capture(sample=False)
+    step_nosample = lambda: tr.train_step(sample=False)
 
     def e2e_step(i):
         o, d, c = host[i % n_host]
@@ -279,7 +274,7 @@ def run_b200(args):
         smp = _lib.NgpSamples()
         smp.rays_o, smp.rays_d = tr.rays_o.data_ptr(), tr.rays_d.data_ptr()
         smp.ray_idx, smp.ts = tr.ray_idx.data_ptr(), tr.ts.data_ptr()
-        smp.n, smp.n_dev = tr.capacity, tr.counters.data_ptr()
+        smp.n, smp.n_dev = tr.capacity, tr.counters[2:].data_ptr()
         L = _lib.lib()
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -334,7 +329,7 @@ def run_b200(args):
     if rank != 0:
         return
     per_update = 9  # kernels of ngp_update_density_grid for one cascade
-    launches = K * 12 + (K // tr.update_interval + 1) * per_update
+    launches = K * 13 + (K // tr.update_interval + 1) * per_update  # gen_rays, march, compact, fwd, 2 composite, loss, scale, bwd, scatter, adam, step_inc + 1 re-march on refresh steps
     line = {
         "metric": "train_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
@@ -358,42 +353,6 @@ def run_b200(args):
         except Exception as e:  # the oracle is only a reported baseline; never let it sink the bench line
             line["cpu_baseline"] = {"unavailable": repr(e)}
     print(json.dumps(line))
-
-
-def make_ddp_step(tr, sample=True):
-    """N>1: [batch+fwd+bwd] graph -> eager NCCL all-reduce of the flat gradient -> [Adam] graph"""
-    import torch
-    s = torch.cuda.Stream()
-    s.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(s):
-        saved = [t.clone() for t in (tr.P, tr.M, tr.V, tr.Ph, tr.G, tr.step_dev)]
-        tr._step_body(sample)
-        for t, v in zip((tr.P, tr.M, tr.V, tr.Ph, tr.G, tr.step_dev), saved):
-            t.copy_(v)
-    torch.cuda.current_stream().wait_stream(s)
-    torch.cuda.synchronize()
-    g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-    g1.register_generator_state(tr.gen)
-    with torch.cuda.graph(g1):
-        if sample:
-            tr.sample_batch()
-        tr.forward()
-        tr.loss_backward()
-    if tr.ddp != "p2p":
-        with torch.cuda.graph(g2):
-            tr.optimizer_step()
-
-    def step():
-        if tr.host_step % tr.update_interval == 0:
-            tr.update_density_grid(warmup=tr.host_step < tr.warmup_steps)
-        g1.replay()
-        if tr.ddp == "p2p":
-            tr.optimizer_step()  # barrier, fused NVLink kernel, barrier, clear gradients
-        else:
-            tr.allreduce()
-            g2.replay()
-        tr.host_step += 1
-    return step
 
 
 def render_fps(render_fn, scene, dev, n_views):

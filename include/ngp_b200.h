@@ -168,6 +168,21 @@ int ngp_net_backward_mlp(const NgpNet* net, const NgpSamples* smp, const float* 
 int ngp_net_backward_scatter(const NgpNet* net, const NgpSamples* smp, const float* loss_scale, float* grad_enc,
                              void* workspace, size_t workspace_bytes, void* stream);
 
+/* Stand-alone module kernels for callers that use the three tinycudann modules one by one, as the
+ * reference's NGP.forward does (models/networks.py:104,144-145); see ngp_pl_b200/tcnn.py.
+ *   ngp_sh_encode        : tcnn.Encoding(SphericalHarmonics deg 4): u in [0,1]^3 (n,3) fp32 -> fp16 (n,16)
+ *   ngp_mlp_rgb_forward  : tcnn.Network 32->64->64->3 on x fp16 (n,32) -> fp16 (n,3)
+ *   ngp_mlp_rgb_backward : dL/dout fp32 (n,3) -> dL/dx fp32 (n,32) (optional) and grad_rgb (+=, fp32 7168)
+ *   ngp_enc_backward     : tcnn.NetworkWithInputEncoding backward from dL/dh fp32 (n,16); forward is
+ *                          ngp_net_forward(want_rgb=0, h_out, feat_save); workspace as ngp_net_backward */
+int ngp_sh_encode(const float* u01, int64_t n, uint16_t* out_half, void* stream);
+int ngp_mlp_rgb_forward(const uint16_t* rgb_params_h, const uint16_t* x_half, int64_t n, int rgb_act, uint16_t* out_half3,
+                        void* stream);
+int ngp_mlp_rgb_backward(const uint16_t* rgb_params_h, const uint16_t* x_half, const float* dL_dout3, int64_t n, int rgb_act,
+                         const float* loss_scale, float* dL_dx, float* grad_rgb, void* stream);
+int ngp_enc_backward(const NgpNet* net, const NgpSamples* smp, const float* dL_dh, const void* feat_save,
+                     const float* loss_scale, float* grad_enc, void* workspace, size_t workspace_bytes, void* stream);
+
 /* loss_scale helper: *scale_out = 2^floor(log2(256 / max(|dL_dsigmas*sigma'|, |dL_drgbs|))) (1 if all zero). */
 int ngp_grad_scale(const float* dL_dsigmas, const float* sigmas, const float* dL_drgbs, int64_t n,
                    float* scratch /* 1 float */, float* scale_out, void* stream);
@@ -198,7 +213,8 @@ typedef struct {
     float* stage_dt;              /* (n_rays*max_samples) */
     int32_t* n_samples;           /* (n_rays) marched samples per ray == rays_a[:,2] */
     int32_t* offsets;             /* (n_rays) exclusive prefix sum == rays_a[:,1] */
-    int32_t* counters;            /* [0] total marched samples (rm_samples), [1] total composited (vr_samples) */
+    int32_t* counters;            /* int32[4]: [0] marched samples (rm_samples), [1] composited (vr_samples) of the step in flight;
+                                     [2],[3] the same, snapshotted by ngp_nerf_loss_grad for the last completed step */
     float* rgb;                   /* (n_rays,3) composited colour incl. background */
     float* opacity;               /* (n_rays) */
     float* depth;                 /* (n_rays) */
@@ -223,6 +239,10 @@ size_t ngp_train_scan_temp_bytes(int n_rays);
 
 /* forward: fills per-ray rgb/opacity/depth (+ws) and everything the backward needs */
 int ngp_render_train_fwd(const NgpNet* net, const NgpTrainCfg* cfg, const NgpTrainBuffers* buf, void* stream);
+/* its two halves: _march (AABB + march + scan + compaction; independent of the weights, so it may overlap the
+ * optimiser of the previous step) and _net (network + compositing). _fwd == _march then _net. */
+int ngp_render_train_march(const NgpTrainCfg* cfg, const NgpTrainBuffers* buf, void* stream);
+int ngp_render_train_net(const NgpNet* net, const NgpTrainCfg* cfg, const NgpTrainBuffers* buf, void* stream);
 
 /* backward from per-ray gradients (dL_ddepth / dL_dws may be NULL = 0); accumulates (+=) into the
  * fp32 gradient vectors laid out like the parameter vectors. */

@@ -126,9 +126,15 @@ SIGNATURES = {
     "ngp_net_backward": (_i, [C.POINTER(NgpNet), C.POINTER(NgpSamples), _P, _P, _P, _P, _P, _P, _P, _sz, _P]),
     "ngp_net_backward_mlp": (_i, [C.POINTER(NgpNet), C.POINTER(NgpSamples), _P, _P, _P, _P, _P, _P, _P, _sz, _P]),
     "ngp_net_backward_scatter": (_i, [C.POINTER(NgpNet), C.POINTER(NgpSamples), _P, _P, _P, _sz, _P]),
+    "ngp_sh_encode": (_i, [_P, _i64, _P, _P]),
+    "ngp_mlp_rgb_forward": (_i, [_P, _P, _i64, _i, _P, _P]),
+    "ngp_mlp_rgb_backward": (_i, [_P, _P, _P, _i64, _i, _P, _P, _P, _P]),
+    "ngp_enc_backward": (_i, [C.POINTER(NgpNet), C.POINTER(NgpSamples), _P, _P, _P, _P, _P, _sz, _P]),
     "ngp_grad_scale": (_i, [_P, _P, _P, _i64, _P, _P, _P]),
     "ngp_train_scan_temp_bytes": (_sz, [_i]),
     "ngp_render_train_fwd": (_i, [C.POINTER(NgpNet), C.POINTER(NgpTrainCfg), C.POINTER(NgpTrainBuffers), _P]),
+    "ngp_render_train_march": (_i, [C.POINTER(NgpTrainCfg), C.POINTER(NgpTrainBuffers), _P]),
+    "ngp_render_train_net": (_i, [C.POINTER(NgpNet), C.POINTER(NgpTrainCfg), C.POINTER(NgpTrainBuffers), _P]),
     "ngp_render_train_bwd": (_i, [C.POINTER(NgpNet), C.POINTER(NgpTrainCfg), C.POINTER(NgpTrainBuffers),
                                   _P, _P, _P, _P, _P, _P, _P]),
     "ngp_nerf_loss_grad": (_i, [C.POINTER(NgpTrainCfg), C.POINTER(NgpTrainBuffers), _P, _P, _P, _P]),

@@ -174,18 +174,28 @@ struct MarchProbe {
     float t_target;  // where an empty visit here jumps to (valid when !occ)
 };
 
+// ONE_CASCADE: with a single cascade both mip_from_pos and mip_from_dt clamp to 0 (min(cascades-1, .)), so
+// mip = 0 and mip_bound = min(2^-1, scale) for every sample: the two frexpf, the scalbnf and the division drop out.
+template <bool ONE_CASCADE>
 __device__ __forceinline__ MarchProbe march_probe(const MarchRay& r, const MarchConst& c, float t) {
     MarchProbe o;
     const float x = __fmaf_rn(r.dx, t, r.ox);
     const float y = __fmaf_rn(r.dy, t, r.oy);
     const float z = __fmaf_rn(r.dz, t, r.oz);
     o.dt = march_dt(t, c);
-    int e_pos, e_dt;
-    frexpf(fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z))), &e_pos);
-    frexpf(__fmul_rn(o.dt, c.gs_f), &e_dt);
-    const int mip = max(min(c.cascades - 1, max(0, e_pos + 1)), min(c.cascades - 1, max(0, e_dt)));
-    const float mip_bound = fminf(scalbnf(1.0f, mip - 1), c.scale);
-    const float mip_bound_inv = __fdiv_rn(1.0f, mip_bound);
+    int mip = 0;
+    float mip_bound, mip_bound_inv;
+    if (ONE_CASCADE) {
+        mip_bound = fminf(0.5f, c.scale);
+        mip_bound_inv = __fdiv_rn(1.0f, mip_bound);
+    } else {
+        int e_pos, e_dt;
+        frexpf(fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z))), &e_pos);
+        frexpf(__fmul_rn(o.dt, c.gs_f), &e_dt);
+        mip = max(min(c.cascades - 1, max(0, e_pos + 1)), min(c.cascades - 1, max(0, e_dt)));
+        mip_bound = fminf(scalbnf(1.0f, mip - 1), c.scale);
+        mip_bound_inv = __fdiv_rn(1.0f, mip_bound);
+    }
     const float vx = __fmul_rn(__fmul_rn(__fmaf_rn(x, mip_bound_inv, 1.0f), 0.5f), c.gs_f);
     const float vy = __fmul_rn(__fmul_rn(__fmaf_rn(y, mip_bound_inv, 1.0f), 0.5f), c.gs_f);
     const float vz = __fmul_rn(__fmul_rn(__fmaf_rn(z, mip_bound_inv, 1.0f), 0.5f), c.gs_f);
@@ -211,7 +221,9 @@ __device__ __forceinline__ MarchProbe march_probe(const MarchRay& r, const March
 // March one ray with a full warp. emit(k, t, dt) is called by the lane owning the k-th sample
 // (k = 0.. in ray order). Returns the number of samples (same in every lane) and leaves in t_resume the
 // chain point the serial marcher would visit next (what raymarching_test stores back into hits_t).
-template <class FEmit>
+// CONST_DT: exp_step_factor == 0 (synthetic scenes): t*0 clamps to dt_lo for every finite t >= 0, so the step
+// is the constant dt_lo and the chain needs one rounded add per point (same value, same rounding).
+template <bool CONST_DT, bool ONE_CASCADE, class FEmit>
 __device__ __forceinline__ int march_ray_warp(const MarchRay& ray, const MarchConst& c, float t_start, float t2,
                                               int max_new, int lane, FEmit emit, float* t_resume = nullptr) {
     int n = 0;
@@ -225,14 +237,14 @@ __device__ __forceinline__ int march_ray_warp(const MarchRay& ray, const MarchCo
         float p = t;
 #pragma unroll
         for (int j = 0; j < 31; ++j) {
-            const float nx = __fadd_rn(p, march_dt(p, c));
+            const float nx = __fadd_rn(p, CONST_DT ? c.dt_lo : march_dt(p, c));
             if (lane > j) p = nx;
         }
-        float t_next = __fadd_rn(p, march_dt(p, c));
+        float t_next = __fadd_rn(p, CONST_DT ? c.dt_lo : march_dt(p, c));
         t_next = __shfl_sync(0xffffffffu, t_next, 31);
         // 2. probe all 32 cells
         const bool valid = p < t2;
-        const MarchProbe pr = march_probe(ray, c, p);
+        const MarchProbe pr = march_probe<ONE_CASCADE>(ray, c, p);
         const unsigned valid_mask = __ballot_sync(0xffffffffu, valid);
         const unsigned occ_mask = __ballot_sync(0xffffffffu, valid && pr.occ);
         // 3. which of them does the serial walk visit?

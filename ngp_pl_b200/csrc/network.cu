@@ -887,64 +887,70 @@ k_ngp_bwd2(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_
 __global__ void __launch_bounds__(SCATTER_THREADS)
 k_grid_scatter_merged(const NgpNet net, const NgpSamples smp, const uint32_t* __restrict__ dfeat, const int64_t dfeat_stride,
                       const float* __restrict__ loss_scale, float* __restrict__ grad_table) {
-    const int level = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int64_t n = sample_count(smp);
     const float inv_scale = loss_scale ? 1.0f / *loss_scale : 1.0f;
-    const uint32_t res = net.meta.res[level];
-    const uint32_t off = net.meta.offset[level];
-    const uint32_t entries = net.meta.offset[level + 1] - off;
-    const bool hashed = (net.meta.hashed_mask >> level) & 1u;
-    const float scale = net.meta.scale[level];
-    const uint32_t* df = dfeat + (int64_t)level * dfeat_stride;
     const int64_t n_pad = (n + 31) & ~(int64_t)31;
+    const int n_levels = net.meta.n_levels;
 
     for (int64_t s = blockIdx.x * (int64_t)SCATTER_THREADS + threadIdx.x; s < n_pad; s += (int64_t)gridDim.x * SCATTER_THREADS) {
         const bool valid = s < n;
+        // the sample position is computed once and reused for all levels
         const SampleIn sm = load_sample(smp, s, valid);
         float u, v, w;
         to_unit(net, sm, u, v, w);
-        const GridCell c = grid_cell(u, v, w, scale);
-        float2 gr = make_float2(0.f, 0.f);
-        if (valid) {
-            gr = unpack_half2(__ldg(df + s));
-            gr.x *= inv_scale;
-            gr.y *= inv_scale;
-        }
-        // corner contributions of this sample
-        float acc[16];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float wk = ((k & 1) ? c.wx : 1.0f - c.wx) * ((k & 2) ? c.wy : 1.0f - c.wy) * ((k & 4) ? c.wz : 1.0f - c.wz);
-            acc[2 * k] = wk * gr.x;
-            acc[2 * k + 1] = wk * gr.y;
-        }
-        // runs of equal cells (an invalid lane never joins a run)
-        const uint32_t px = __shfl_up_sync(0xffffffffu, c.gx, 1), py = __shfl_up_sync(0xffffffffu, c.gy, 1),
-                       pz = __shfl_up_sync(0xffffffffu, c.gz, 1);
-        const bool pvalid = __shfl_up_sync(0xffffffffu, valid ? 1 : 0, 1) != 0;
-        const bool head = lane == 0 || !valid || !pvalid || px != c.gx || py != c.gy || pz != c.gz;
-        const unsigned heads = __ballot_sync(0xffffffffu, head);
-        if (heads != 0xffffffffu) {
-            // last lane of my run = lane before the next head
-            const unsigned later = lane == 31 ? 0u : (heads >> (lane + 1));
-            const int run_end = later ? lane + __ffs(later) - 1 : 31;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const bool take = lane + d <= run_end;
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const float o = __shfl_down_sync(0xffffffffu, acc[k], d);
-                    if (take) acc[k] += o;
-                }
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        for (int level = 0; level < n_levels; ++level) {
+            const uint32_t res = net.meta.res[level];
+            const uint32_t off = net.meta.offset[level];
+            const uint32_t entries = net.meta.offset[level + 1] - off;
+            const bool hashed = (net.meta.hashed_mask >> level) & 1u;
+            const GridCell c = grid_cell(u, v, w, net.meta.scale[level]);
+            float2 gr = make_float2(0.f, 0.f);
+            if (valid) {
+                gr = unpack_half2(__ldg(dfeat + (int64_t)level * dfeat_stride + s));
+                gr.x *= inv_scale;
+                gr.y *= inv_scale;
             }
-        }
-        if (valid && head) {
+            float acc[16];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const uint32_t qx = c.gx + (k & 1), qy = c.gy + ((k >> 1) & 1), qz = c.gz + ((k >> 2) & 1);
-                const uint32_t idx = off + grid_corner_index(qx, qy, qz, res, entries, hashed);
-                red_add_f32x2(grad_table + 2 * (size_t)idx, acc[2 * k], acc[2 * k + 1]);
+                const float wk = ((k & 1) ? c.wx : 1.0f - c.wx) * ((k & 2) ? c.wy : 1.0f - c.wy) * ((k & 4) ? c.wz : 1.0f - c.wz);
+                acc[2 * k] = wk * gr.x;
+                acc[2 * k + 1] = wk * gr.y;
+            }
+            // runs of equal cells (an invalid lane never joins a run)
+            const uint32_t px = __shfl_up_sync(0xffffffffu, c.gx, 1), py = __shfl_up_sync(0xffffffffu, c.gy, 1),
+                           pz = __shfl_up_sync(0xffffffffu, c.gz, 1);
+            const bool pvalid = lane > 0 && ((vmask >> (lane - 1)) & 1u);
+            const bool head = lane == 0 || !valid || !pvalid || px != c.gx || py != c.gy || pz != c.gz;
+            const unsigned heads = __ballot_sync(0xffffffffu, head);
+            if (heads != 0xffffffffu) {
+                const unsigned later = lane == 31 ? 0u : (heads >> (lane + 1));
+                const int run_end = later ? lane + __ffs(later) - 1 : 31;
+                // longest run in the warp bounds the depth of the segmented reduction (warp-uniform)
+                unsigned cont = ~heads;  // bit i set: lane i continues the run of lane i-1
+                int max_run = 1;
+                while (cont) {
+                    cont &= cont >> 1;
+                    ++max_run;
+                }
+                for (int d = 1; d < max_run; d <<= 1) {
+                    const bool take = lane + d <= run_end;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const float o = __shfl_down_sync(0xffffffffu, acc[k], d);
+                        if (take) acc[k] += o;
+                    }
+                }
+            }
+            if (valid && head) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t qx = c.gx + (k & 1), qy = c.gy + ((k >> 1) & 1), qz = c.gz + ((k >> 2) & 1);
+                    const uint32_t idx = off + grid_corner_index(qx, qy, qz, res, entries, hashed);
+                    red_add_f32x2(grad_table + 2 * (size_t)idx, acc[2 * k], acc[2 * k + 1]);
+                }
             }
         }
     }
@@ -1010,10 +1016,9 @@ extern "C" int ngp_net_backward_scatter(const NgpNet* net, const NgpSamples* smp
     if (smp->n == 0) return 0;
     const int64_t n_mtiles = (smp->n + 15) / 16;
     int64_t gx = (smp->n + SCATTER_THREADS - 1) / SCATTER_THREADS;
-    const int64_t cap = (int64_t)ngp_sm_count() * 8 / net->meta.n_levels + 1;
+    const int64_t cap = (int64_t)ngp_sm_count() * 8;
     if (gx > cap) gx = cap;
-    dim3 sg((unsigned)gx, (unsigned)net->meta.n_levels);
-    k_grid_scatter_merged<<<sg, SCATTER_THREADS, 0, (cudaStream_t)stream>>>(
+    k_grid_scatter_merged<<<(unsigned)gx, SCATTER_THREADS, 0, (cudaStream_t)stream>>>(
         *net, *smp, (const uint32_t*)workspace, n_mtiles * 16, loss_scale, grad_enc + NGP_DENSITY_MLP_PARAMS);
     NGP_CHECK_LAUNCH();
     return 0;

@@ -16,6 +16,7 @@ static inline int one_thread_per_ray_block(int n_rays) { return n_rays >= 148 * 
 // 1. AABB + near clamp + jittered march, ONE pass: samples go to a per-ray staging row
 //    (reference intersection.cu:25-56, rendering.py:29, raymarching.cu:166-235)
 // -------------------------------------------------------------------------------------------------
+template <bool CONST_DT, bool ONE_CASCADE>
 __global__ void k_train_march(const NgpTrainCfg cfg, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                               const float* __restrict__ noise, const uint8_t* __restrict__ bitfield,
                               float* __restrict__ stage_t, float* __restrict__ stage_dt, int* __restrict__ n_samples) {
@@ -38,7 +39,7 @@ __global__ void k_train_march(const NgpTrainCfg cfg, const float* __restrict__ r
     const float t = march_jitter(t1, noise[r], c);
     float* st = stage_t + (size_t)r * cfg.max_samples;
     float* sd = stage_dt + (size_t)r * cfg.max_samples;
-    const int n = march_ray_warp(ray, c, t, t2, cfg.max_samples, lane, [&](int k, float ts, float dts) {
+    const int n = march_ray_warp<CONST_DT, ONE_CASCADE>(ray, c, t, t2, cfg.max_samples, lane, [&](int k, float ts, float dts) {
         st[k] = ts;
         sd[k] = dts;
     });
@@ -133,19 +134,42 @@ static int check_train_args(const NgpNet* net, const NgpTrainCfg* cfg, const Ngp
     return 0;
 }
 
-extern "C" int ngp_render_train_fwd(const NgpNet* net, const NgpTrainCfg* cfg, const NgpTrainBuffers* b, void* stream) {
-    int rc = check_train_args(net, cfg, b);
+// first half of the forward: AABB + march + prefix sum + compaction. Depends only on the rays, the jitter
+// and the occupancy bitfield (NOT on the network weights), so a trainer may run it for step i+1 while the
+// optimiser of step i is still updating the weights.
+extern "C" int ngp_render_train_march(const NgpTrainCfg* cfg, const NgpTrainBuffers* b, void* stream) {
+    NgpNet dummy;
+    int rc = check_train_args(&dummy, cfg, b);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int n = cfg->n_rays;
-    k_train_march<<<ngp_div_up((int64_t)n * 32, 128), 128, 0, st>>>(*cfg, b->rays_o, b->rays_d, b->noise, b->density_bitfield, b->stage_t,
-                                                     b->stage_dt, b->n_samples);
+    // exp_step_factor == 0 with dt_lo <= dt_hi: every step equals dt_lo (clamp(0, lo, hi))
+    const bool const_dt = cfg->exp_step_factor == 0.0f &&
+                          1.73205080757f / (float)cfg->max_samples <= cfg->scale * 3.46410161514f / (float)cfg->grid_size;
+    const dim3 mg(ngp_div_up((int64_t)n * 32, 128));
+#define NGP_LAUNCH_MARCH(CD, OC)                                                                                        \
+    k_train_march<CD, OC><<<mg, 128, 0, st>>>(*cfg, b->rays_o, b->rays_d, b->noise, b->density_bitfield, b->stage_t, \
+                                              b->stage_dt, b->n_samples)
+    if (const_dt && cfg->cascades == 1) NGP_LAUNCH_MARCH(true, true);
+    else if (const_dt) NGP_LAUNCH_MARCH(true, false);
+    else if (cfg->cascades == 1) NGP_LAUNCH_MARCH(false, true);
+    else NGP_LAUNCH_MARCH(false, false);
+#undef NGP_LAUNCH_MARCH
     NGP_CHECK_LAUNCH();
     size_t temp_bytes = b->scan_temp_bytes;
     NGP_CUDA(cub::DeviceScan::ExclusiveSum(b->scan_temp, temp_bytes, b->n_samples, b->offsets, n, st));
     k_train_compact<<<ngp_div_up((int64_t)n * 32, 256), 256, 0, st>>>(*cfg, b->stage_t, b->stage_dt, b->n_samples, b->offsets,
                                                                        b->ray_idx, b->ts, b->deltas, b->counters);
     NGP_CHECK_LAUNCH();
+    return 0;
+}
+
+// second half of the forward: network on the marched samples + ragged compositing
+extern "C" int ngp_render_train_net(const NgpNet* net, const NgpTrainCfg* cfg, const NgpTrainBuffers* b, void* stream) {
+    int rc = check_train_args(net, cfg, b);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = cfg->n_rays;
     const NgpSamples smp = train_samples(cfg, b);
     rc = ngp_net_forward(net, &smp, 1, b->sigmas, b->rgbs, nullptr, b->feat_save, stream);
     if (rc) return rc;
@@ -154,6 +178,12 @@ extern "C" int ngp_render_train_fwd(const NgpNet* net, const NgpTrainCfg* cfg, c
                                                                             b->ws, b->counters);
     NGP_CHECK_LAUNCH();
     return 0;
+}
+
+extern "C" int ngp_render_train_fwd(const NgpNet* net, const NgpTrainCfg* cfg, const NgpTrainBuffers* b, void* stream) {
+    int rc = ngp_render_train_march(cfg, b, stream);
+    if (rc) return rc;
+    return ngp_render_train_net(net, cfg, b, stream);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -246,7 +276,7 @@ extern "C" int ngp_render_train_bwd(const NgpNet* net, const NgpTrainCfg* cfg, c
 // -------------------------------------------------------------------------------------------------
 __global__ void k_nerf_loss_grad(const NgpTrainCfg cfg, const float* __restrict__ rgb, const float* __restrict__ opacity,
                                  const float* __restrict__ rgb_gt, float* __restrict__ dL_drgb, float* __restrict__ dL_dopacity,
-                                 float* __restrict__ scalars) {
+                                 float* __restrict__ scalars, int* __restrict__ counters) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     float se = 0.f, ent = 0.f;
     if (r < cfg.n_rays) {
@@ -268,13 +298,19 @@ __global__ void k_nerf_loss_grad(const NgpTrainCfg cfg, const float* __restrict_
         atomicAdd(&scalars[2], se);
         atomicAdd(&scalars[3], ent);
     }
+    // snapshot of this step's sample counts (counters[0..1] are reused by the next step's march, which a
+    // trainer may run ahead of time)
+    if (r == 0) {
+        counters[2] = counters[0];
+        counters[3] = counters[1];
+    }
 }
 
 extern "C" int ngp_nerf_loss_grad(const NgpTrainCfg* cfg, const NgpTrainBuffers* b, const float* rgb_gt, float* dL_drgb,
                                   float* dL_dopacity, void* stream) {
     if (!cfg || !b || !rgb_gt || !dL_drgb || !dL_dopacity || cfg->n_rays < 1) return NGP_EINVAL;
     k_nerf_loss_grad<<<ngp_div_up(cfg->n_rays, 256), 256, 0, (cudaStream_t)stream>>>(*cfg, b->rgb, b->opacity, rgb_gt, dL_drgb,
-                                                                                      dL_dopacity, b->scalars);
+                                                                                      dL_dopacity, b->scalars, b->counters);
     NGP_CHECK_LAUNCH();
     return 0;
 }
@@ -337,8 +373,10 @@ extern "C" int ngp_adam_step(float* params, float* grads, float* exp_avg, float*
         return NGP_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     if (n > 0) {
+        // 3 resident blocks per SM are enough to saturate HBM and leave room for the next step's march, which a
+        // trainer overlaps with this kernel on another stream
         int grid = ngp_div_up((n >> 2) + 1, 256);
-        const int cap = ngp_sm_count() * 8;
+        const int cap = ngp_sm_count() * 3;
         if (grid > cap) grid = cap;
         k_adam<<<grid, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, (__half*)params_half, n, lr_dev, step_dev, beta1, beta2,
                                       eps, grad_mul);
@@ -429,7 +467,7 @@ extern "C" int ngp_adam_step_p2p(int world, int rank, const uint64_t* peer_grads
     const int64_t hi4 = lo4 + base + (rank < extra ? 1 : 0);
     if (hi4 > lo4) {
         int grid = ngp_div_up(hi4 - lo4, 256);
-        const int cap = ngp_sm_count() * 8;
+        const int cap = ngp_sm_count() * 4;
         if (grid > cap) grid = cap;
         k_adam_p2p<<<grid, 256, 0, st>>>(pp, world, params, exp_avg, exp_avg_sq, lo4, hi4, lr_dev, step_dev, beta1, beta2,
                                           eps, 1.0f / (float)world);

@@ -105,24 +105,116 @@ class _NGPForward(torch.autograd.Function):
         return None, None, g_enc, g_rgb, None
 
 
+def _pow2_scale(t):
+    """power-of-two loss scale 2^floor(log2(256 / max|t|)) as a device scalar (no host sync); 1 if t == 0"""
+    amax = t.detach().abs().max().float()
+    s = torch.exp2(torch.floor(torch.log2(256.0 / amax.clamp_min(1e-30)))).clamp(2.0 ** -60, 2.0 ** 60)
+    return torch.where(amax > 0, s, torch.ones_like(s)).reshape(1).contiguous()
+
+
+def _unit_net(module):
+    """NgpNet of a stand-alone tcnn.NetworkWithInputEncoding: its input is already in [0,1]^3"""
+    net = _lib.NgpNet()
+    enc_h = module.half_params()
+    net.enc_params_h = enc_h.data_ptr()
+    net.rgb_params_h = None
+    net.meta = module.meta
+    for k in range(3):
+        net.xyz_min[k], net.xyz_max[k] = 0.0, 1.0
+    net.rgb_act = 1
+    return net, enc_h
+
+
 class _DensityFeatures(torch.autograd.Function):
-    """tcnn.NetworkWithInputEncoding.forward stand-alone: x01 (N,3) -> fp16 (N,16)."""
+    """tcnn.NetworkWithInputEncoding.forward stand-alone: x01 (N,3) in [0,1] -> fp16 (N,16)
+    (reference call site: networks.py:104  h = self.xyz_encoder(x))."""
 
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, x01, params, module):
-        raise NotImplementedError("stand-alone tcnn.NetworkWithInputEncoding call: use NGP.density / NGP.forward")
+        x01 = x01.float().contiguous()  # (cast_inputs only acts under autocast)
+        n, dev = x01.shape[0], x01.device
+        with torch.cuda.device(dev):
+            net, keep = _unit_net(module)
+            smp = _samples_struct(x01, None)
+            h = torch.empty(n, 16, device=dev, dtype=torch.float16)
+            sig = torch.empty(n, device=dev, dtype=torch.float32)
+            need = any(ctx.needs_input_grad)
+            feat = torch.empty(feat_save_bytes(n), device=dev, dtype=torch.uint8) if need else None
+            rc = _lib.lib().ngp_net_forward(C.byref(net), C.byref(smp), 0, sig.data_ptr(), None, h.data_ptr(),
+                                            feat.data_ptr() if feat is not None else None, _st())
+            _lib.check(rc, "net_forward(features)")
+        ctx.module, ctx.feat = module, feat
+        ctx.save_for_backward(x01)
+        return h
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dL_dh):
+        (x01,) = ctx.saved_tensors
+        module = ctx.module
+        n, dev = x01.shape[0], x01.device
+        g = torch.zeros_like(module.params)
+        if n > 0:
+            with torch.cuda.device(dev):
+                net, keep = _unit_net(module)
+                smp = _samples_struct(x01, None)
+                d = dL_dh.float().contiguous()
+                scale = _pow2_scale(d)
+                L = _lib.lib()
+                ws_bytes = L.ngp_net_backward_workspace(n)
+                ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+                rc = L.ngp_enc_backward(C.byref(net), C.byref(smp), d.data_ptr(), ctx.feat.data_ptr(), scale.data_ptr(),
+                                        g.data_ptr(), ws.data_ptr(), ws_bytes, _st())
+                _lib.check(rc, "enc_backward")
+        return None, g, None
 
 
 class _RgbMlp(torch.autograd.Function):
+    """tcnn.Network(32 -> 3).forward stand-alone: x (N,32) -> fp16 (N,3) (reference call site networks.py:145)."""
+
     @staticmethod
-    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float16)
     def forward(ctx, x, params, module):
-        raise NotImplementedError("stand-alone tcnn.Network call: use NGP.forward")
+        x = x.half().contiguous()  # (cast_inputs only acts under autocast)
+        n, dev = x.shape[0], x.device
+        with torch.cuda.device(dev):
+            wh = module.half_params()
+            out = torch.empty(n, 3, device=dev, dtype=torch.float16)
+            rc = _lib.lib().ngp_mlp_rgb_forward(wh.data_ptr(), x.data_ptr(), n, module.rgb_act, out.data_ptr(), _st())
+            _lib.check(rc, "mlp_rgb_forward")
+        ctx.module = module
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dL_dout):
+        (x,) = ctx.saved_tensors
+        module = ctx.module
+        n, dev = x.shape[0], x.device
+        g = torch.zeros_like(module.params)
+        dx = torch.zeros(n, 32, device=dev, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        if n > 0:
+            with torch.cuda.device(dev):
+                wh = module.half_params()
+                d = dL_dout.float().contiguous()
+                scale = _pow2_scale(d)
+                rc = _lib.lib().ngp_mlp_rgb_backward(wh.data_ptr(), x.data_ptr(), d.data_ptr(), n, module.rgb_act,
+                                                     scale.data_ptr(), dx.data_ptr() if dx is not None else None,
+                                                     g.data_ptr(), _st())
+                _lib.check(rc, "mlp_rgb_backward")
+        return dx, g, None
 
 
-def sh_encode(x):
-    raise NotImplementedError("stand-alone tcnn.Encoding call: use NGP.forward")
+def sh_encode(u):
+    """tcnn.Encoding(SphericalHarmonics, degree 4): u in [0,1]^3 (N,3) -> fp16 (N,16); no gradient (the
+    reference feeds it normalised directions that do not require grad, networks.py:143-144)."""
+    u = u.detach().float().contiguous()
+    out = torch.empty(u.shape[0], 16, device=u.device, dtype=torch.float16)
+    with torch.cuda.device(u.device):
+        _lib.check(_lib.lib().ngp_sh_encode(u.data_ptr(), u.shape[0], out.data_ptr(), _st()), "sh_encode")
+    return out
 
 
 class NGP(nn.Module):
@@ -222,6 +314,32 @@ class NGP(nn.Module):
             coords2 = vren.morton3D_invert(indices2.int())
             cells += [(torch.cat([indices1, indices2]), torch.cat([coords1, coords2]))]
         return cells
+
+    @torch.no_grad()
+    def mark_invisible_cells(self, K, poses, img_wh, chunk=64 ** 3):
+        """Cells that no training camera sees (or that lie closer than NEAR_DISTANCE in front of one) get
+        density -1 and are never revived; `count_grid` keeps the fraction of cameras covering each cell (used
+        by erode=True). Semantics of reference networks.py:197-238; called once before training (train.py:154-157).
+        K (3,3) intrinsics, poses (N,3,4) camera-to-world, img_wh (w, h)."""
+        G = self.grid_size
+        n_cams = poses.shape[0]
+        R_wc = poses[:, :3, :3].transpose(1, 2)            # world -> camera rotations (N,3,3)
+        t_wc = -(R_wc @ poses[:, :3, 3:])                   # (N,3,1)
+        self.count_grid = torch.zeros_like(self.density_grid)
+        w, h = float(img_wh[0]), float(img_wh[1])
+        for c, (indices, coords) in enumerate(self.get_all_cells()):
+            s, half_cell = self._cascade_extent(c)
+            for i in range(0, indices.shape[0], chunk):
+                idx = indices[i:i + chunk]
+                centres = ((coords[i:i + chunk] / (G - 1) * 2 - 1) * (s - half_cell)).T       # (3,M) world
+                uvd = K @ (R_wc @ centres + t_wc)                                               # (N,3,M)
+                depth = uvd[:, 2]
+                uv = uvd[:, :2] / uvd[:, 2:]
+                inside = (depth >= 0) & (uv[:, 0] >= 0) & (uv[:, 0] < w) & (uv[:, 1] >= 0) & (uv[:, 1] < h)
+                seen = (inside & (depth >= NEAR_DISTANCE)).sum(0) / n_cams
+                too_close = (inside & (depth < NEAR_DISTANCE)).any(0)
+                self.count_grid[c, idx] = seen
+                self.density_grid[c, idx] = torch.where((seen > 0) & ~too_close, 0.0, -1.0)
 
     def _cascade_extent(self, c):
         """half extent of cascade c and half a cell of it (reference networks.py:250-251)"""

@@ -51,7 +51,8 @@ def shard_range(n_items, world_size, rank):
 class Trainer:
     def __init__(self, model: NGP, n_rays=8192, lr=1e-2, exp_step_factor=0.0, bg=(1.0, 1.0, 1.0), lambda_opacity=1e-3,
                  T_threshold=1e-4, betas=(0.9, 0.999), eps=1e-15, max_total_samples=None, update_interval=16,
-                 warmup_steps=256, process_group=None, world_size=1, rank=0, seed=0, materialize_ws=False, ddp="nccl"):
+                 warmup_steps=256, process_group=None, world_size=1, rank=0, seed=0, materialize_ws=False, ddp="nccl",
+                 lambda_distortion=0.0):
         self.model = model
         dev = model.density_bitfield.device
         if dev.type != "cuda":
@@ -63,6 +64,9 @@ class Trainer:
         self.update_interval, self.warmup_steps = update_interval, warmup_steps
         self.pg, self.world_size, self.rank = process_group, int(world_size), int(rank)
         self.exp_step_factor = float(exp_step_factor)
+        self.lambda_distortion = float(lambda_distortion)  # reference opt.py:25 --distortion_loss_w (0 = off)
+        if self.lambda_distortion > 0:
+            materialize_ws = True
         self.host_step = 0
         self.seed = seed
         # "nccl": all_reduce of the flat gradient + full Adam on every rank;
@@ -164,6 +168,15 @@ class Trainer:
             self.scalars = torch.zeros(8, **f32)
             self.dL_drgb = torch.zeros(N, 3, **f32)
             self.dL_dopacity = torch.zeros(N, **f32)
+            if self.lambda_distortion > 0:
+                # DistortionLoss (reference losses.py:6-37) on the fused path: per-sample scans + dL/dws
+                self.rays_a = torch.zeros(N, 3, device=dev, dtype=torch.int64)
+                self.rays_a[:, 0] = torch.arange(N, device=dev)
+                self.dist_loss = torch.zeros(N, **f32)
+                self.dist_dL = torch.full((N,), self.lambda_distortion / N, **f32)  # d(mean(lambda*loss))/dloss
+                self.ws_inc = torch.empty(cap, **f32)
+                self.wts_inc = torch.empty(cap, **f32)
+                self.dL_dws = torch.zeros(cap, **f32)
             scan_bytes = L.ngp_train_scan_temp_bytes(N)
             self.scan_temp = torch.empty(scan_bytes, device=dev, dtype=torch.uint8)
             b = _lib.NgpTrainBuffers()
@@ -188,7 +201,9 @@ class Trainer:
             self.grid_ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
             self.gen = torch.Generator(device=dev)
             self.gen.manual_seed(seed + 1000 * self.rank)
-        self.graph = None
+        self.graph = False
+        self._graph_samples = None
+        self._premarched = False
         self.bank = None
 
     # ------------------------------------------------------------------------------------------------------
@@ -232,18 +247,39 @@ class Trainer:
         self.rays_d.copy_(rays_d, non_blocking=True)
         self.rgb_gt.copy_(rgb_gt, non_blocking=True)
 
-    def forward(self):
+    def march(self):
+        """first half of the forward: start jitter + AABB + march + scan + compaction (independent of the weights)"""
         self.noise.uniform_(0, 1, generator=self.gen)
-        _lib.check(_lib.lib().ngp_render_train_fwd(C.byref(self.net), C.byref(self.cfg), C.byref(self.buf), self._st()),
-                   "render_train_fwd")
+        _lib.check(_lib.lib().ngp_render_train_march(C.byref(self.cfg), C.byref(self.buf), self._st()), "render_train_march")
+
+    def network(self):
+        """second half of the forward: fused network kernel on the marched samples + ragged compositing"""
+        _lib.check(_lib.lib().ngp_render_train_net(C.byref(self.net), C.byref(self.cfg), C.byref(self.buf), self._st()),
+                   "render_train_net")
+
+    def forward(self):
+        self.march()
+        self.network()
 
     def loss_backward(self):
         L = _lib.lib()
         self.scalars[2:4].zero_()
         _lib.check(L.ngp_nerf_loss_grad(C.byref(self.cfg), C.byref(self.buf), self.rgb_gt.data_ptr(),
                                         self.dL_drgb.data_ptr(), self.dL_dopacity.data_ptr(), self._st()), "nerf_loss_grad")
+        dws = None
+        if self.lambda_distortion > 0:
+            self.rays_a[:, 1] = self.offsets
+            self.rays_a[:, 2] = self.n_samples
+            N, cap = self.n_rays, self.capacity
+            _lib.check(L.ngp_distortion_loss_fw(self.ws.data_ptr(), self.deltas.data_ptr(), self.ts.data_ptr(),
+                                                self.rays_a.data_ptr(), N, cap, self.dist_loss.data_ptr(),
+                                                self.ws_inc.data_ptr(), self.wts_inc.data_ptr(), self._st()), "distortion_fw")
+            _lib.check(L.ngp_distortion_loss_bw(self.dist_dL.data_ptr(), self.ws_inc.data_ptr(), self.wts_inc.data_ptr(),
+                                                self.ws.data_ptr(), self.deltas.data_ptr(), self.ts.data_ptr(),
+                                                self.rays_a.data_ptr(), N, cap, self.dL_dws.data_ptr(), self._st()), "distortion_bw")
+            dws = self.dL_dws.data_ptr()
         _lib.check(L.ngp_render_train_bwd(C.byref(self.net), C.byref(self.cfg), C.byref(self.buf), self.dL_drgb.data_ptr(),
-                                          self.dL_dopacity.data_ptr(), None, None, self.G.data_ptr(),
+                                          self.dL_dopacity.data_ptr(), None, dws, self.G.data_ptr(),
                                           self.G[self.n_enc:].data_ptr(), self._st()), "render_train_bwd")
 
     def allreduce(self):
@@ -284,42 +320,94 @@ class Trainer:
             lo, hi = self.shard_bounds(r)
             dist.broadcast(self.P[lo:hi], src=r, group=self.pg)
 
-    def _step_body(self, sample):
+    # ---- one optimiser step ----------------------------------------------------------------------------------
+    def _prepare(self, sample):
         if sample:
             self.sample_batch()
-        self.forward()
+        self.march()
+
+    def _compute(self):
+        self.network()
         self.loss_backward()
+
+    def _update(self):
         self.allreduce()
         self.optimizer_step()
 
+    def _step_body(self, sample):
+        self._prepare(sample)
+        self._compute()
+        self._update()
+
     def capture(self, sample=True):
-        """record one optimiser step into a CUDA graph (warm up on a side stream first)"""
-        s = torch.cuda.Stream(self.dev)
-        s.wait_stream(torch.cuda.current_stream(self.dev))
+        """Record the step into CUDA graphs. Three graphs instead of one so that the weight-independent front
+        of the NEXT step (batch assembly + march) can replay on a side stream while the optimiser of THIS step
+        (Adam / all-reduce / the fused NVLink kernel) runs on the main stream:
+            g_prepare = [device RNG, ngp_gen_rays, march, scan, compaction]
+            g_compute = [network fwd, compositing, NeRFLoss, compositing bwd, loss scale, MLP bwd, scatter]
+            g_update  = [Adam]   (NCCL all-reduce / the p2p kernel and its barriers are launched eagerly)"""
+        dev = self.dev
+        s = torch.cuda.Stream(dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(s):
-            # one eager run so lazy initialisation (cudaFuncSetAttribute, NCCL communicators) is done
+            # one eager run so lazy initialisation (cudaFuncSetAttribute, NCCL / symmetric-memory setup) is done
             saved = [t.clone() for t in (self.P, self.M, self.V, self.Ph, self.G, self.step_dev)]
             self._step_body(sample)
+            if self.ddp == "p2p":
+                self.hG.barrier(channel=0)
             for t, v in zip((self.P, self.M, self.V, self.Ph, self.G, self.step_dev), saved):
                 t.copy_(v)
-        torch.cuda.current_stream(self.dev).wait_stream(s)
-        torch.cuda.synchronize(self.dev)
-        g = torch.cuda.CUDAGraph()
-        self.gen_states = None
-        g.register_generator_state(self.gen)
-        with torch.cuda.graph(g):
-            self._step_body(sample)
-        self.graph = g
+            if self.ddp == "p2p":
+                self.hG.barrier(channel=0)
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        self.g_prepare, self.g_compute, self.g_update = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), None
+        self.g_prepare.register_generator_state(self.gen)
+        with torch.cuda.graph(self.g_prepare):
+            self._prepare(sample)
+        with torch.cuda.graph(self.g_compute):
+            self._compute()
+        if self.ddp != "p2p":
+            self.g_update = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_update):
+                self.optimizer_step()
+        self.graph = True
         self._graph_samples = sample
+        self._side = torch.cuda.Stream(dev)
+        self._premarched = False
 
     def train_step(self, sample=True):
         """one full training step incl. the occupancy refresh cadence of reference train.py:160-163"""
-        if self.host_step % self.update_interval == 0:
+        refresh = self.host_step % self.update_interval == 0
+        if refresh:
             self.update_density_grid(warmup=self.host_step < self.warmup_steps)
-        if self.graph is not None and self._graph_samples == sample:
-            self.graph.replay()
-        else:
+        if not (self.graph and self._graph_samples == sample):
             self._step_body(sample)
+            self._premarched = False
+            self.host_step += 1
+            return
+        main = torch.cuda.current_stream(self.dev)
+        if not self._premarched:
+            self.g_prepare.replay()
+        elif refresh:
+            # the batch was assembled and marched ahead of time against the previous bitfield: march the SAME rays
+            # and jitter again so that the step sees the refreshed grid, exactly like the reference's ordering
+            _lib.check(_lib.lib().ngp_render_train_march(C.byref(self.cfg), C.byref(self.buf), self._st()), "render_train_march")
+        self.g_compute.replay()
+        # overlap: the next step's batch + march (side stream) with this step's optimiser (main stream)
+        ahead = sample and ((self.host_step + 1) % self.update_interval != 0)
+        if ahead:
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                self.g_prepare.replay()
+        self.allreduce()
+        if self.g_update is not None:
+            self.g_update.replay()
+        else:
+            self.optimizer_step()
+        if ahead:
+            main.wait_stream(self._side)
+        self._premarched = ahead
         self.host_step += 1
 
     # ---- read-backs (these DO synchronise; not used inside the timed loop) -----------------------------------
@@ -328,5 +416,10 @@ class Trainer:
         s = self.scalars.tolist()
         n = self.n_rays
         mse = s[2] / (3 * n)
-        return dict(rm_samples=c[0], vr_samples=c[1], mse=mse, psnr=-10 * math.log10(max(mse, 1e-12)),
-                    loss=mse + self.cfg.lambda_opacity * s[3] / n)
+        loss = mse + self.cfg.lambda_opacity * s[3] / n
+        out = dict(rm_samples=c[2], vr_samples=c[3], mse=mse, psnr=-10 * math.log10(max(mse, 1e-12)))
+        if self.lambda_distortion > 0:
+            out["distortion"] = self.lambda_distortion * float(self.dist_loss.mean())
+            loss += out["distortion"]
+        out["loss"] = loss
+        return out

@@ -26,21 +26,41 @@ def available():
     return bool(glob.glob(os.path.join(REF, "vren*.so"))) and os.path.isdir(os.path.join(REF, "ngp_pl", "models"))
 
 
-_cached = None
+def python_available():
+    return os.path.isdir(os.path.join(REF, "ngp_pl", "models"))
 
 
-def load_reference():
-    global _cached
-    if _cached is not None:
-        return _cached
-    if not available():
-        raise RuntimeError("oracle/_ref is not built (run oracle/build_ref.py where /root/reference exists)")
+_cached = {}
+
+
+def load_reference(drop_in=False):
+    """drop_in=False: the reference's Python on the REFERENCE's compiled vren + the tinycudann stand-in.
+    drop_in=True : the reference's Python on ngp_pl_b200.vren + ngp_pl_b200.tcnn (the drop-in claim under test)."""
+    if drop_in in _cached:
+        return _cached[drop_in]
     import torch  # noqa: F401  (must be imported before the extension)
-    if REF not in sys.path:
-        sys.path.insert(0, REF)
-    vren = importlib.import_module("vren")
-    from . import tcnn_standin
-    sys.modules["tinycudann"] = tcnn_standin
+    if drop_in:
+        if not python_available():
+            raise RuntimeError("reference python is not staged under oracle/_ref/ngp_pl")
+        import ngp_pl_b200.tcnn as tcnn_impl
+        import ngp_pl_b200.vren as vren
+        saved = {k: sys.modules.get(k) for k in ("vren", "tinycudann")}
+        sys.modules["vren"] = vren
+        sys.modules["tinycudann"] = tcnn_impl
+    else:
+        if not available():
+            raise RuntimeError("oracle/_ref is not built (run oracle/build_ref.py where /root/reference exists)")
+        if REF not in sys.path:
+            sys.path.insert(0, REF)
+        saved = {k: sys.modules.get(k) for k in ("vren", "tinycudann")}
+        for k in ("vren",):
+            if k in sys.modules and getattr(sys.modules[k], "__name__", "") != "vren":
+                del sys.modules[k]
+        if "vren" in sys.modules and getattr(sys.modules["vren"], "__file__", "") and "ngp_pl_b200" in sys.modules["vren"].__file__:
+            del sys.modules["vren"]
+        vren = importlib.import_module("vren")
+        from . import tcnn_standin
+        sys.modules["tinycudann"] = tcnn_standin
     ts = types.ModuleType("torch_scatter")
 
     def segment_csr(src, indptr):
@@ -55,10 +75,10 @@ def load_reference():
     pkg = os.path.join(REF, "ngp_pl")
     if pkg not in sys.path:
         sys.path.insert(0, pkg)
-    # the reference's packages are top-level `models`, `losses`, `metrics`
+    # the reference's packages are top-level `models`, `losses`, `metrics`; always import a FRESH copy so that the
+    # two bindings (reference kernels / our kernels) get separate module objects
     for name in ("models", "models.custom_functions", "models.rendering", "models.networks", "losses", "metrics"):
-        if name in sys.modules and not getattr(sys.modules[name], "__file__", "").startswith(pkg):
-            del sys.modules[name]
+        sys.modules.pop(name, None)
     r = Reference()
     r.vren = vren
     r.custom_functions = importlib.import_module("models.custom_functions")
@@ -67,5 +87,13 @@ def load_reference():
     r.losses = importlib.import_module("losses")
     r.NGP = r.networks.NGP
     r.render = r.rendering.render
-    _cached = r
+    # leave no reference-named modules behind (the loaded copies keep their own globals)
+    for name in ("models", "models.custom_functions", "models.rendering", "models.networks", "losses", "metrics"):
+        sys.modules.pop(name, None)
+    for k, v in saved.items():
+        if v is None:
+            sys.modules.pop(k, None)
+        else:
+            sys.modules[k] = v
+    _cached[drop_in] = r
     return r

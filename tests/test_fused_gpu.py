@@ -265,3 +265,40 @@ def test_fused_nvlink_optimizer_step_two_gpus(tmp_path):
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:]
     assert "MISMATCH" not in r.stdout
+
+
+def test_fused_trainer_with_distortion_loss_matches_autograd():
+    """lambda_distortion > 0 on the fused path (ws materialised, ngp_distortion_loss_fw/bw feeding dL_dws into the
+    compositing backward) against render() + NeRFLoss(lambda_distortion) + autograd"""
+    import ctypes as C
+    from ngp_pl_b200 import _lib, synth
+    from ngp_pl_b200.losses import NeRFLoss
+    from ngp_pl_b200.trainer import Trainer
+    from ngp_pl_b200.models.rendering import render
+    from ngp_pl_b200.models.custom_functions import RayMarcher
+    scene = synth.mip360_scene(0)
+    n, lam = 1024, 1e-2
+    model = make_model(scene)
+    o_np, d_np = cases.rays_from_scene(scene, n, 43, extra_edge_cases=False)
+    o, d = torch.as_tensor(o_np).cuda(), torch.as_tensor(d_np).cuda()
+    gt = torch.rand(n, 3, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+    tr = Trainer(model, n_rays=n, exp_step_factor=scene.exp_step_factor, bg=(0.0,) * 3, lambda_distortion=lam)
+    tr.set_batch(o, d, gt)
+    noise = torch.rand(n, device="cuda", generator=torch.Generator("cuda").manual_seed(2))
+    tr.noise.copy_(noise)
+    _lib.check(_lib.lib().ngp_render_train_fwd(C.byref(tr.net), C.byref(tr.cfg), C.byref(tr.buf), tr._st()), "fwd")
+    tr.loss_backward()
+    torch.cuda.synchronize()
+    st = tr.stats()
+    RayMarcher.noise_override = noise
+    try:
+        model.zero_grad()
+        res = render(model, o, d, exp_step_factor=scene.exp_step_factor)
+    finally:
+        RayMarcher.noise_override = None
+    loss = sum(v.mean() for v in NeRFLoss(lambda_distortion=lam)(res, {"rgb": gt}).values())
+    loss.backward()
+    assert abs(loss.item() - st["loss"]) < 1e-4 * max(1.0, abs(loss.item()))
+    g_ref = torch.cat([model.xyz_encoder.params.grad, model.rgb_net.params.grad])
+    s = g_ref.abs().max().item()
+    assert (g_ref - tr.G).abs().max().item() < 3e-3 * s

@@ -95,3 +95,52 @@ def test_test_render_matches_reference(ref):
     # a ray's early termination can flip on an fp16-level sigma difference; totals must be close
     a, b = int(r_ref["total_samples"]), int(r_my["total_samples"])
     assert abs(a - b) <= 0.01 * a + 8
+
+
+def test_losses_match_reference(ref):
+    """NeRFLoss incl. the distortion term (reference losses.py) through both stacks on the same render"""
+    if ref is None:
+        pytest.skip("oracle/_ref not built on this box")
+    from ngp_pl_b200 import synth
+    from ngp_pl_b200.losses import NeRFLoss
+    from ngp_pl_b200.models.rendering import render
+    scene = synth.mip360_scene(0)
+    mine, theirs = make_pair(ref, scene.scale, scene)
+    o, d = _rays(scene, 1024, 32)
+    torch.manual_seed(7)
+    r_my = render(mine, o, d, exp_step_factor=scene.exp_step_factor)
+    tgt = torch.rand(o.shape[0], 3, device="cuda")
+    mine.zero_grad()
+    l_my = NeRFLoss(lambda_distortion=1e-3)(r_my, {"rgb": tgt})
+    # the reference's loss module evaluated on OUR render results (its vren = the reference kernels)
+    r_det = {k: (v.detach().clone().requires_grad_(v.is_floating_point() and v.dim() > 0) if torch.is_tensor(v) else v)
+             for k, v in r_my.items()}
+    l_ref = ref.losses.NeRFLoss(lambda_distortion=1e-3)(r_det, {"rgb": tgt})
+    for k in ("rgb", "opacity", "distortion"):
+        assert torch.allclose(l_my[k].float(), l_ref[k].float(), rtol=1e-4, atol=3e-8), k
+    # gradient of the distortion term w.r.t. ws through both Functions
+    g_my = torch.autograd.grad(l_my["distortion"].sum(), r_my["ws"], retain_graph=True)[0]
+    g_ref = torch.autograd.grad(l_ref["distortion"].sum(), r_det["ws"])[0]
+    assert torch.allclose(g_my, g_ref, rtol=1e-4, atol=3e-8)
+
+
+def test_mark_invisible_cells_matches_reference(ref):
+    if ref is None:
+        pytest.skip("oracle/_ref not built on this box")
+    from ngp_pl_b200 import synth
+    from ngp_pl_b200.models.networks import NGP
+    scale = 2.0
+    mine, theirs = NGP(scale).cuda(), ref.NGP(scale).cuda()
+    G = 128
+    coords = torch.stack(torch.meshgrid(*[torch.arange(G, dtype=torch.int32, device="cuda")] * 3, indexing="ij"), -1).reshape(-1, 3)
+    for m in (mine, theirs):
+        m.register_buffer("density_grid", torch.zeros(m.cascades, G ** 3, device="cuda"))
+        m.register_buffer("grid_coords", coords)
+    Kd = synth.intrinsics(W=200, H=150, fx=180.0)
+    K = torch.tensor([[Kd["fx"], 0, Kd["cx"]], [0, Kd["fy"], Kd["cy"]], [0, 0, 1]], device="cuda")
+    poses = torch.as_tensor(synth.camera_poses(6, radius=1.2)).cuda()
+    mine.mark_invisible_cells(K, poses, (200, 150))
+    theirs.mark_invisible_cells(K, poses, (200, 150))
+    assert torch.equal(mine.density_grid, theirs.density_grid)
+    assert torch.allclose(mine.count_grid, theirs.count_grid)
+    assert 0 < (mine.density_grid < 0).float().mean().item() < 1
