@@ -408,21 +408,23 @@ def run_reference(args):
     gx = torch.stack(torch.meshgrid(*[torch.arange(G, dtype=torch.int32, device=dev)] * 3, indexing="ij"), -1).reshape(-1, 3)
     model.register_buffer("grid_coords", gx)
     opt = torch.optim.Adam(model.parameters(), lr=1e-2, eps=1e-15)
+    scaler = torch.amp.GradScaler("cuda")
     loss_fn = ref.losses.NeRFLoss(lambda_distortion=0)
     state = {"step": 0, "res": None}
 
     def step():
-        # PL runs training_step under fp16 autocast (Trainer(precision=16), train.py:274); the stand-in
-        # computes with fp32 gradients, so no GradScaler is needed (which only favours this arm)
+        # PL runs training_step under fp16 autocast with its GradScaler (Trainer(precision=16), train.py:274): the
+        # network outputs are fp16, so without loss scaling the per-sample gradients underflow
+        o, d, rgb = bank.sample(N_RAYS)  # fp32 rays (the reference builds them under autocast(dtype=float32), ray_utils.py:46)
         with torch.autocast("cuda", dtype=torch.float16):
             if state["step"] % 16 == 0:
                 model.update_density_grid(0.01 * 1024 / 3 ** 0.5, warmup=state["step"] < 256)
-            o, d, rgb = bank.sample(N_RAYS)
             res = ref.render(model, o, d)
             loss = sum(v.mean() for v in loss_fn(res, {"rgb": rgb}).values())
         opt.zero_grad(set_to_none=True)
-        loss.backward()
-        opt.step()
+        scaler.scale(loss).backward()
+        scaler.step(opt)
+        scaler.update()
         state["step"] += 1
         state["res"] = (res, rgb)
     pretrain = args.pretrain if args.pretrain is not None else 1000

@@ -54,7 +54,8 @@ int ngp_morton3D_invert(const int* indices, int n, int* coords, void* stream);
 /* vren.raymarching_train (binding.cpp:60-81, raymarching.cu:166-332). hits_t is (n_rays,2). Outputs:
  * rays_a int64 (n_rays,3) = [ray_idx,start_idx,N_samples] ordered by ray index; xyzs,dirs (>=total,3);
  * deltas,ts (>=total); counter int32[2] = [total_samples, n_rays]. Rows past `total` are not written. */
-size_t ngp_raymarching_train_workspace(int n_rays);
+size_t ngp_raymarching_train_workspace(int n_rays);                     /* minimum (serial two-pass kernels) */
+size_t ngp_raymarching_train_workspace2(int n_rays, int max_samples);   /* + staging rows: enables the warp-per-ray marcher */
 int ngp_raymarching_train(const float* rays_o, const float* rays_d, const float* hits_t,
                           const uint8_t* density_bitfield, int cascades, float scale, float exp_step_factor,
                           const float* noise, int grid_size, int max_samples, int n_rays,

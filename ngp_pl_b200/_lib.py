@@ -112,6 +112,7 @@ SIGNATURES = {
     "ngp_morton3D": (_i, [_P, _i, _P, _P]),
     "ngp_morton3D_invert": (_i, [_P, _i, _P, _P]),
     "ngp_raymarching_train_workspace": (_sz, [_i]),
+    "ngp_raymarching_train_workspace2": (_sz, [_i, _i]),
     "ngp_raymarching_train": (_i, [_P, _P, _P, _P, _i, _f, _f, _P, _i, _i, _i, _P, _P, _P, _P, _P, _P, _P, _sz, _P]),
     "ngp_raymarching_test": (_i, [_P, _P, _P, _P, _P, _i, _f, _f, _i, _i, _i, _i, _P, _P, _P, _P, _P, _P]),
     "ngp_composite_train_fw": (_i, [_P, _P, _P, _P, _P, _f, _i, _i64, _P, _P, _P, _P, _P, _P]),

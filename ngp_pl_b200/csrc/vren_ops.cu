@@ -282,11 +282,76 @@ static size_t scan_temp_bytes(int n) {
     return (bytes + 255) & ~(size_t)255;
 }
 
-extern "C" size_t ngp_raymarching_train_workspace(int n_rays) {
+// Warp-per-ray variant (march.cuh: march_ray_warp, bit-exact with the serial loop): ONE march into a per-ray
+// staging row of (t, dt), prefix sum, then a coalesced expansion to xyzs/dirs/deltas/ts. Used whenever the
+// staging rows fit the workspace budget; the serial two-pass kernels above remain for very large ray counts.
+#define NGP_MARCH_STAGE_BUDGET (512ull << 20)
+
+template <bool CONST_DT, bool ONE_CASCADE>
+__global__ void k_march_train_stage(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                    const float* __restrict__ hits_t, const float* __restrict__ noise,
+                                    const uint8_t* __restrict__ bitfield, int cascades, int grid_size, float scale, float esf,
+                                    int max_samples, int n_rays, float2* __restrict__ stage, int* __restrict__ n_samples) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= n_rays) return;
+    const MarchConst c = make_march_const(bitfield, cascades, grid_size, max_samples, scale, esf, scale);
+    const MarchRay ray = make_march_ray(rays_o[3 * r], rays_o[3 * r + 1], rays_o[3 * r + 2],
+                                        rays_d[3 * r], rays_d[3 * r + 1], rays_d[3 * r + 2]);
+    const float t2 = hits_t[2 * r + 1];
+    const float t = march_jitter(hits_t[2 * r], noise[r], c);
+    float2* st = stage + (size_t)r * max_samples;
+    const int n = march_ray_warp<CONST_DT, ONE_CASCADE>(ray, c, t, t2, max_samples, lane,
+                                                        [&](int k, float ts, float dts) { st[k] = make_float2(ts, dts); });
+    if (lane == 0) n_samples[r] = n;
+}
+
+__global__ void k_march_train_expand(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                     const float2* __restrict__ stage, int max_samples, int n_rays,
+                                     const int* __restrict__ n_samples, const int* __restrict__ offsets,
+                                     int64_t* __restrict__ rays_a, float* __restrict__ xyzs, float* __restrict__ dirs,
+                                     float* __restrict__ deltas, float* __restrict__ ts, int* __restrict__ counter) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= n_rays) return;
+    const int n = n_samples[r];
+    const int64_t start = offsets[r];
+    if (lane == 0) {
+        rays_a[3 * r] = r;
+        rays_a[3 * r + 1] = start;
+        rays_a[3 * r + 2] = n;
+        if (r == n_rays - 1) {
+            counter[0] = (int)(start + n);
+            counter[1] = n_rays;
+        }
+    }
+    const float ox = rays_o[3 * r], oy = rays_o[3 * r + 1], oz = rays_o[3 * r + 2];
+    const float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
+    const float2* st = stage + (size_t)r * max_samples;
+    for (int k = lane; k < n; k += 32) {
+        const float2 v = st[k];
+        const int64_t s = start + k;
+        xyzs[3 * s] = __fmaf_rn(dx, v.x, ox);
+        xyzs[3 * s + 1] = __fmaf_rn(dy, v.x, oy);
+        xyzs[3 * s + 2] = __fmaf_rn(dz, v.x, oz);
+        dirs[3 * s] = dx; dirs[3 * s + 1] = dy; dirs[3 * s + 2] = dz;
+        ts[s] = v.x;
+        deltas[s] = v.y;
+    }
+}
+
+static bool march_use_stage(int n_rays, int max_samples) {
+    return (unsigned long long)n_rays * (unsigned long long)max_samples * sizeof(float2) <= NGP_MARCH_STAGE_BUDGET;
+}
+
+extern "C" size_t ngp_raymarching_train_workspace2(int n_rays, int max_samples) {
     if (n_rays <= 0) return 256;
     const size_t ints = (((size_t)n_rays * sizeof(int)) + 255) & ~(size_t)255;
-    return 2 * ints + scan_temp_bytes(n_rays);
+    size_t bytes = 2 * ints + scan_temp_bytes(n_rays);
+    if (max_samples > 0 && march_use_stage(n_rays, max_samples)) bytes += (size_t)n_rays * max_samples * sizeof(float2) + 256;
+    return bytes;
 }
+extern "C" size_t ngp_raymarching_train_workspace(int n_rays) { return ngp_raymarching_train_workspace2(n_rays, 0); }
 
 static inline int march_block(int n_rays) { return n_rays >= 148 * 128 * 4 ? 128 : 32; }
 
@@ -307,6 +372,26 @@ extern "C" int ngp_raymarching_train(const float* rays_o, const float* rays_d, c
     int* offsets = (int*)((char*)workspace + ints);
     void* temp = (char*)workspace + 2 * ints;
     size_t temp_bytes = scan_temp_bytes(n_rays);
+    // the caller sized the workspace with ngp_raymarching_train_workspace2: warp-per-ray path with staging rows
+    if (march_use_stage(n_rays, max_samples) && workspace_bytes >= ngp_raymarching_train_workspace2(n_rays, max_samples)) {
+        float2* stage = (float2*)((((uintptr_t)temp + temp_bytes) + 255) & ~(uintptr_t)255);
+        const bool const_dt = exp_step_factor == 0.0f && 1.73205080757f / (float)max_samples <= scale * 3.46410161514f / (float)grid_size;
+        const dim3 mg(ngp_div_up((int64_t)n_rays * 32, 128));
+#define NGP_LAUNCH_STAGE(CD, OC)                                                                                           \
+    k_march_train_stage<CD, OC><<<mg, 128, 0, st>>>(rays_o, rays_d, hits_t, noise, density_bitfield, cascades, grid_size, \
+                                                    scale, exp_step_factor, max_samples, n_rays, stage, n_samples)
+        if (const_dt && cascades == 1) NGP_LAUNCH_STAGE(true, true);
+        else if (const_dt) NGP_LAUNCH_STAGE(true, false);
+        else if (cascades == 1) NGP_LAUNCH_STAGE(false, true);
+        else NGP_LAUNCH_STAGE(false, false);
+#undef NGP_LAUNCH_STAGE
+        NGP_CHECK_LAUNCH();
+        NGP_CUDA(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, n_samples, offsets, n_rays, st));
+        k_march_train_expand<<<mg, 128, 0, st>>>(rays_o, rays_d, stage, max_samples, n_rays, n_samples, offsets, rays_a, xyzs,
+                                                 dirs, deltas, ts, counter);
+        NGP_CHECK_LAUNCH();
+        return 0;
+    }
     const int bs = march_block(n_rays);
     k_march_train_count<<<ngp_div_up(n_rays, bs), bs, 0, st>>>(rays_o, rays_d, hits_t, noise, density_bitfield, cascades,
                                                                 grid_size, scale, exp_step_factor, max_samples, n_rays,

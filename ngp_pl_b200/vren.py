@@ -115,7 +115,7 @@ def raymarching_train(rays_o, rays_d, hits_t, density_bitfield, cascades, scale,
         ts = torch.empty(cap, device=dev, dtype=torch.float32)
         counter = torch.empty(2, device=dev, dtype=torch.int32)
         L = _lib.lib()
-        ws_bytes = L.ngp_raymarching_train_workspace(n_rays)
+        ws_bytes = L.ngp_raymarching_train_workspace2(n_rays, int(max_samples))
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
         rc = L.ngp_raymarching_train(_p(_f32(rays_o)), _p(_f32(rays_d)), _p(_f32(hits_t)), _p(density_bitfield),
                                      int(cascades), float(scale), float(exp_step_factor), _p(_f32(noise)),
