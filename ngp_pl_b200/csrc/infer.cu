@@ -3,12 +3,16 @@
 //
 // The reference loops on the host: march N more samples for every alive ray, evaluate the network,
 // composite, drop converged rays (boolean-mask compaction => >= 3 host syncs per round, tens of rounds
-// per image). Here the alive list, the per-round sample counts and the convergence test all stay on
-// the device: the host enqueues a FIXED schedule of rounds (2,2,4,4,...,64,64,... samples per ray per
-// round) and late rounds simply find an empty alive list. Each ray still sees exactly the reference's
-// sample sequence (raymarching_test_kernel semantics, incl. its `cascades`-as-scale quirk) and the same
-// front-to-back accumulation order, so results differ from the reference only by the fp16-level network
-// difference and by where the chunk boundaries fall (T is resumed as 1 - opacity, volumerendering.cu:230).
+// per image). Here the alive list (ping-pong), the per-round sample counts and the convergence test all
+// stay on the device. Per round every alive ray receives the reference's sample budget
+// max(min(N_rays / N_alive, 64), min_samples) (rendering.py:73), computed ON the device from the alive
+// counter and clamped to a fair share of the sample capacity, so long rays are never starved. The host
+// enqueues `n_rounds` rounds at a time and reads only the alive counter between batches
+// (ngp_render_infer: first_round / n_rounds / finish / alive_count_out). Each ray still sees exactly the
+// reference's sample sequence (raymarching_test_kernel semantics, incl. its `cascades`-as-scale quirk) and
+// the same front-to-back accumulation order, so results differ from the reference only by the fp16-level
+// network difference and by where the chunk boundaries fall (T is resumed as 1 - opacity,
+// volumerendering.cu:230).
 #include "common.cuh"
 #include "march.cuh"
 #include "../../include/ngp_b200.h"
