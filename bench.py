@@ -275,6 +275,11 @@ def run_b200(args):
         smp.rays_o, smp.rays_d = tr.rays_o.data_ptr(), tr.rays_d.data_ptr()
         smp.ray_idx, smp.ts = tr.ray_idx.data_ptr(), tr.ts.data_ptr()
         smp.n, smp.n_dev = tr.capacity, tr.counters[2:].data_ptr()
+        # the backward visits only the composited samples (live list of the last step; counters[5] = its length)
+        smp_b = _lib.NgpSamples.from_buffer_copy(smp)
+        n_bwd = stats["bw_samples"]
+        if tr.live_idx is not None:
+            smp_b.live_idx, smp_b.n_live_dev = tr.live_idx.data_ptr(), tr.counters[5:].data_ptr()
         L = _lib.lib()
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -290,10 +295,10 @@ def run_b200(args):
             return float(np.mean(ts_))
         st = torch.cuda.current_stream().cuda_stream
         ws = (tr.bwd_ws.data_ptr(), tr.bwd_ws.numel())
-        t_mlp = timed(lambda: L.ngp_net_backward_mlp(C.byref(tr.net), C.byref(smp), tr.dsigmas.data_ptr(), tr.drgbs.data_ptr(),
+        t_mlp = timed(lambda: L.ngp_net_backward_mlp(C.byref(tr.net), C.byref(smp_b), tr.dsigmas.data_ptr(), tr.drgbs.data_ptr(),
                                                      tr.feat_save.data_ptr(), tr.scalars[1:].data_ptr(), tr.G.data_ptr(),
                                                      tr.G[tr.n_enc:].data_ptr(), ws[0], ws[1], st))
-        t_sc = timed(lambda: L.ngp_net_backward_scatter(C.byref(tr.net), C.byref(smp), tr.scalars[1:].data_ptr(), tr.G.data_ptr(),
+        t_sc = timed(lambda: L.ngp_net_backward_scatter(C.byref(tr.net), C.byref(smp_b), tr.scalars[1:].data_ptr(), tr.G.data_ptr(),
                                                         ws[0], ws[1], st))
         t_fwd = timed(lambda: L.ngp_net_forward(C.byref(tr.net), C.byref(smp), 1, tr.sigmas.data_ptr(), tr.rgbs.data_ptr(),
                                                 None, tr.feat_save.data_ptr(), st))
@@ -306,16 +311,19 @@ def run_b200(args):
             except Exception:
                 traffic = {}
 
-        def entry(kernel, bound, ms_, alg, peak, unit, note):
+        def entry(kernel, bound, ms_, n_, per_sample, peak, unit, note):
+            alg = n_ * per_sample
             ach = alg / (ms_ * 1e-3) / (1e9 if unit == "GB/s" else 1e12)
             return {"kernel": kernel, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
                     "traffic": traffic.get(kernel + "_dram_bytes_per_launch"), "ms_per_launch": ms_,
-                    "samples_per_launch": n_samples, "algorithmic": note}
+                    "samples_per_launch": n_, "algorithmic": note}
         # algorithmic work per sample (SURVEY.md section 8d / DESIGN.md): forward 512 B of table reads, scatter 1,024 B of
         # table-gradient read-modify-write, MLP backward 40,960 FLOP (dgrad + wgrad; the forward recompute is not counted)
-        ks = [entry("k_ngp_fwd", "hbm", t_fwd, n_samples * 512.0, hbm, "GB/s", "512 B/sample table gathers"),
-              entry("k_grid_scatter_merged", "hbm", t_sc, n_samples * 1024.0, hbm, "GB/s", "1,024 B/sample gradient RMW"),
-              entry("k_ngp_bwd", "tensor", t_mlp, n_samples * 40960.0, tf, "TFLOP/s", "40,960 FLOP/sample dgrad+wgrad")]
+        ks = [entry("k_ngp_fwd", "hbm", t_fwd, n_samples, 512.0, hbm, "GB/s", "512 B/sample table gathers, every marched sample"),
+              entry("k_grid_scatter_merged", "hbm", t_sc, n_bwd, 1024.0, hbm, "GB/s",
+                    "1,024 B/sample gradient RMW, composited samples only"),
+              entry("k_ngp_bwd", "tensor", t_mlp, n_bwd, 40960.0, tf, "TFLOP/s",
+                    "40,960 FLOP/sample dgrad+wgrad, composited samples only")]
         roof = dict(max(ks, key=lambda e: e["ms_per_launch"]))  # the dominant kernel of the step
         roof["peak_source"] = which
         roof["kernels"] = ks
@@ -342,6 +350,7 @@ def run_b200(args):
                    "pretrain_steps": pretrain,
                    "l2": "no explicit flush: each step streams params+grads+Adam moments (~230 MB) > 126 MB L2",
                    "samples_per_ray_marched": stats["rm_samples"] / N_RAYS, "samples_per_ray_composited": stats["vr_samples"] / N_RAYS,
+                   "samples_per_ray_in_backward": stats["bw_samples"] / N_RAYS,
                    "train_psnr_last_batch": stats["psnr"]},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof,
     }

@@ -20,7 +20,7 @@ extern "C" {
 #endif
 
 #define NGP_MAX_LEVELS 16
-#define NGP_ABI_VERSION 1
+#define NGP_ABI_VERSION 2
 
 int ngp_abi_version(void);
 
@@ -140,6 +140,11 @@ typedef struct {
     const float* ts;
     int64_t n;            /* number of samples, or the CAPACITY when n_dev is set */
     const int32_t* n_dev; /* optional device int32: the kernels read the sample count from here (no host sync) */
+    /* backward only (ngp_net_backward*, default kernel with feat_save): visit just the samples live_idx[0 .. *n_live_dev),
+     * i.e. those whose upstream gradient can be non-zero -- the samples past a ray's termination receive exactly
+     * zero gradient from composite_train_bw (volumerendering.cu:87-151) and contribute +0 to every sum. NULL = all. */
+    const int32_t* live_idx;
+    const int32_t* n_live_dev;
 } NgpSamples;
 
 /* Fused forward of NGP.forward (networks.py:132-153): hash gather + trilinear + density MLP +
@@ -214,8 +219,9 @@ typedef struct {
     float* stage_dt;              /* (n_rays*max_samples) */
     int32_t* n_samples;           /* (n_rays) marched samples per ray == rays_a[:,2] */
     int32_t* offsets;             /* (n_rays) exclusive prefix sum == rays_a[:,1] */
-    int32_t* counters;            /* int32[4]: [0] marched samples (rm_samples), [1] composited (vr_samples) of the step in flight;
-                                     [2],[3] the same, snapshotted by ngp_nerf_loss_grad for the last completed step */
+    int32_t* counters;            /* int32[8]: [0] marched samples (rm_samples), [1] composited (vr_samples) of the step in flight;
+                                     [2],[3] the same, snapshotted by ngp_nerf_loss_grad for the last completed step;
+                                     [4] length of live_idx (written by the backward), [5] its snapshot, [6..7] reserved */
     float* rgb;                   /* (n_rays,3) composited colour incl. background */
     float* opacity;               /* (n_rays) */
     float* depth;                 /* (n_rays) */
@@ -228,6 +234,8 @@ typedef struct {
     float* ws;                    /* (S) optional (NULL: not materialised) */
     float* dsigmas;               /* (S)   backward scratch */
     float* drgbs;                 /* (S,3) backward scratch */
+    int32_t* live_idx;            /* (S) optional: samples with a non-zero upstream gradient, built by the compositing
+                                     backward; the network backward then visits only those */
     void* feat_save;              /* ceil32(S)*64 bytes */
     float* scalars;               /* [0] amax scratch, [1] loss scale, [2] sum sq err, [3] sum opacity entropy */
     void* scan_temp;

@@ -9,6 +9,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libngp_b200.so")
+ABI_VERSION = 2  # NGP_ABI_VERSION in include/ngp_b200.h
 
 NGP_MAX_LEVELS = 16
 NGP_DENSITY_MLP_PARAMS = 3072
@@ -46,6 +47,8 @@ class NgpSamples(C.Structure):
         ("ts", C.c_void_p),
         ("n", C.c_int64),
         ("n_dev", C.c_void_p),
+        ("live_idx", C.c_void_p),
+        ("n_live_dev", C.c_void_p),
     ]
 
 
@@ -92,7 +95,7 @@ class NgpTrainBuffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "rays_o", "rays_d", "noise", "density_bitfield",
         "stage_t", "stage_dt", "n_samples", "offsets", "counters", "rgb", "opacity", "depth",
-        "ray_idx", "ts", "deltas", "sigmas", "rgbs", "ws", "dsigmas", "drgbs", "feat_save", "scalars",
+        "ray_idx", "ts", "deltas", "sigmas", "rgbs", "ws", "dsigmas", "drgbs", "live_idx", "feat_save", "scalars",
         "scan_temp")] + [("scan_temp_bytes", C.c_size_t), ("bwd_workspace", C.c_void_p), ("bwd_workspace_bytes", C.c_size_t)]
 
 
@@ -164,7 +167,7 @@ def lib():
             fn = getattr(h, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if h.ngp_abi_version() != 1:
+        if h.ngp_abi_version() != ABI_VERSION:
             raise RuntimeError("ngp_pl_b200: ABI version mismatch, rebuild libngp_b200.so")
         _lib = h
     return _lib

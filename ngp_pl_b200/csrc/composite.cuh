@@ -68,11 +68,12 @@ __device__ __forceinline__ CompositeOut composite_ray_warp(int n, float T_thresh
     return o;
 }
 
-// Backward of the above for one ray by one warp.
+// Backward of the above for one ray by one warp. Returns the number of composited samples (the leading samples of
+// the ray, terminating one included): only those can receive a non-zero gradient.
 //   dsig(i, v) / dcol(i, float3) store the per-sample gradients (0 for samples past termination).
 //   dws(i) is dL/dws_i (pass a functor returning 0 when no loss touches ws); wsv(i) = forward ws_i.
 template <class FSig, class FDlt, class FT, class FCol, class FDws, class FWs, class FPutS, class FPutC>
-__device__ __forceinline__ void composite_ray_warp_bwd(int n, float T_threshold, int lane,
+__device__ __forceinline__ int composite_ray_warp_bwd(int n, float T_threshold, int lane,
                                                        float dO, float dD, float3 dC,
                                                        float O, float D, float3 C,
                                                        FSig sig, FDlt dlt, FT tt, FCol col, FDws dws, FWs wsv,
@@ -86,6 +87,7 @@ __device__ __forceinline__ void composite_ray_warp_bwd(int n, float T_threshold,
     float pr = 0.f, pg = 0.f, pb = 0.f, pd = 0.f, ps = 0.f;  // inclusive prefixes carried between trips
     bool done = false;
     int base = 0;
+    int n_comp = 0;
     for (; base < n && !done; base += 32) {
         const int i = base + lane;
         const bool valid = i < n;
@@ -125,6 +127,7 @@ __device__ __forceinline__ void composite_ray_warp_bwd(int n, float T_threshold,
                 dsig(i, 0.f);
             }
         }
+        n_comp += __popc(__ballot_sync(0xffffffffu, comp));
         const unsigned term = __ballot_sync(0xffffffffu, valid && !(T_inc > T_threshold));
         done = term != 0u;
         T_carry = __shfl_sync(0xffffffffu, T_inc, 31);
@@ -138,4 +141,5 @@ __device__ __forceinline__ void composite_ray_warp_bwd(int n, float T_threshold,
         dcol(i, make_float3(0.f, 0.f, 0.f));
         dsig(i, 0.f);
     }
+    return n_comp;
 }

@@ -274,7 +274,7 @@ extern "C" int ngp_render_infer(const NgpNet* net, const NgpInferCfg* cfg, const
         NGP_CHECK_LAUNCH();
         NgpSamples smp;
         smp.xyzs = nullptr; smp.dirs = nullptr; smp.rays_o = rays_o; smp.rays_d = rays_d; smp.ray_idx = ray_idx; smp.ts = ts;
-        smp.n = cfg->max_round_samples; smp.n_dev = state + 2;
+        smp.n = cfg->max_round_samples; smp.n_dev = state + 2; smp.live_idx = nullptr; smp.n_live_dev = nullptr;
         int rc = ngp_net_forward(net, &smp, 1, sigmas, rgbs, nullptr, nullptr, stream);
         if (rc) return rc;
         k_infer_composite<<<grid, bs, 0, st>>>(*cfg, sigmas, rgbs, deltas, ts, ray_start, ray_n, t_cur, t_end, alive[cur],

@@ -84,6 +84,16 @@ __device__ __forceinline__ int64_t sample_count(const NgpSamples& s) {
     return s.n;
 }
 
+// Backward-only compaction: when live_idx is given, the backward kernels visit samples live_idx[0 .. *n_live_dev)
+// only (the ones whose upstream gradient can be non-zero) and index their per-sample outputs by that position.
+__device__ __forceinline__ int64_t bwd_count(const NgpSamples& s) {
+    if (s.live_idx) {
+        const int64_t v = (int64_t)__ldg(s.n_live_dev);
+        return v < s.n ? (v < 0 ? 0 : v) : s.n;
+    }
+    return sample_count(s);
+}
+
 __device__ __forceinline__ SampleIn load_sample(const NgpSamples& s, int64_t i, bool valid) {
     SampleIn o;
     if (!valid) {
@@ -675,7 +685,8 @@ k_ngp_bwd2(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_
     load_weights_fwd(S.wf, wd, wr, threadIdx.x, B2_THREADS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
-    const int64_t n = sample_count(smp);
+    const int64_t n = bwd_count(smp);
+    const int32_t* __restrict__ live = smp.live_idx;
     const int64_t n_mtiles = (n + 15) / 16;
     const int64_t n_blks = (n_mtiles + B2_WARPS - 1) / B2_WARPS;
     const float scale = loss_scale ? *loss_scale : 1.0f;
@@ -696,23 +707,42 @@ k_ngp_bwd2(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_
         bool valid[2];
         float up_sig[2] = {0.f, 0.f}, up_c0[2] = {0.f, 0.f}, up_c1[2] = {0.f, 0.f};
         SampleIn sm[2];
+        int64_t src[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int64_t row = base + g + 8 * h;
             valid[h] = row < n;
-            sm[h] = load_sample(smp, row, valid[h]);
+            src[h] = valid[h] ? (live ? (int64_t)__ldg(live + row) : row) : 0;
+            sm[h] = load_sample(smp, src[h], valid[h]);
             if (valid[h]) {
                 if (q == 0) {
-                    up_sig[h] = __ldg(dL_dsigmas + row);
-                    up_c0[h] = __ldg(dL_drgbs + 3 * row);
-                    up_c1[h] = __ldg(dL_drgbs + 3 * row + 1);
+                    up_sig[h] = __ldg(dL_dsigmas + src[h]);
+                    up_c0[h] = __ldg(dL_drgbs + 3 * src[h]);
+                    up_c1[h] = __ldg(dL_drgbs + 3 * src[h] + 1);
                 } else if (q == 1) {
-                    up_c0[h] = __ldg(dL_drgbs + 3 * row + 2);
+                    up_c0[h] = __ldg(dL_drgbs + 3 * src[h] + 2);
                 }
             }
         }
         uint32_t featA[1][2][4];
-        if (base < n) {
+        if (live) {
+            // rows come from arbitrary forward tiles: pick this lane's four words of each row out of the forward's
+            // fragment-order save (word x/z = row g, y/w = row g+8 of the tile that holds the sample)
+            const uint32_t* fs = reinterpret_cast<const uint32_t*>(feat_save);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int64_t t2 = (src[h] >> 4) * 2;
+                const int r = (int)(src[h] & 15);
+                const int64_t w0 = (r & 7) * 4 + q;
+                const int sub = r >> 3;
+#pragma unroll
+                for (int kt = 0; kt < 2; ++kt) {
+                    const uint32_t* p = fs + ((t2 + kt) * 32 + w0) * 4 + sub;
+                    featA[0][kt][h] = valid[h] ? __ldg(p) : 0u;
+                    featA[0][kt][2 + h] = valid[h] ? __ldg(p + 2) : 0u;
+                }
+            }
+        } else if (base < n) {
 #pragma unroll
             for (int kt = 0; kt < 2; ++kt) {
                 const uint4 v = __ldg(feat_save + (mtile * 2 + kt) * 32 + lane);
@@ -888,15 +918,16 @@ __global__ void __launch_bounds__(SCATTER_THREADS)
 k_grid_scatter_merged(const NgpNet net, const NgpSamples smp, const uint32_t* __restrict__ dfeat, const int64_t dfeat_stride,
                       const float* __restrict__ loss_scale, float* __restrict__ grad_table) {
     const int lane = threadIdx.x & 31;
-    const int64_t n = sample_count(smp);
+    const int64_t n = bwd_count(smp);
     const float inv_scale = loss_scale ? 1.0f / *loss_scale : 1.0f;
     const int64_t n_pad = (n + 31) & ~(int64_t)31;
     const int n_levels = net.meta.n_levels;
 
     for (int64_t s = blockIdx.x * (int64_t)SCATTER_THREADS + threadIdx.x; s < n_pad; s += (int64_t)gridDim.x * SCATTER_THREADS) {
         const bool valid = s < n;
-        // the sample position is computed once and reused for all levels
-        const SampleIn sm = load_sample(smp, s, valid);
+        // the sample position is computed once and reused for all levels (dfeat is indexed by s, the position by
+        // the sample it stands for)
+        const SampleIn sm = load_sample(smp, (valid && smp.live_idx) ? (int64_t)__ldg(smp.live_idx + s) : s, valid);
         float u, v, w;
         to_unit(net, sm, u, v, w);
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
@@ -990,6 +1021,7 @@ extern "C" int ngp_net_backward_mlp(const NgpNet* net, const NgpSamples* smp, co
         variant = e ? atoi(e) : 1;
     }
     const int64_t n_mtiles = (smp->n + 15) / 16;
+    if (smp->live_idx && (!smp->n_live_dev || variant == 0 || !feat_save)) return NGP_EINVAL;  // live list: k_ngp_bwd2 only
     if (variant == 0 || !feat_save) {
         const int64_t n_blks = (n_mtiles + BWD_WARPS - 1) / BWD_WARPS;
         const int grid = (int)(n_blks < (int64_t)ngp_sm_count() ? n_blks : ngp_sm_count());
@@ -1012,7 +1044,7 @@ extern "C" int ngp_net_backward_scatter(const NgpNet* net, const NgpSamples* smp
                                         void* workspace, size_t workspace_bytes, void* stream) {
     int rc = check_bwd_args(net, smp, workspace, workspace_bytes);
     if (rc) return rc;
-    if (!grad_enc) return NGP_EINVAL;
+    if (!grad_enc || (smp->live_idx && !smp->n_live_dev)) return NGP_EINVAL;
     if (smp->n == 0) return 0;
     const int64_t n_mtiles = (smp->n + 15) / 16;
     int64_t gx = (smp->n + SCATTER_THREADS - 1) / SCATTER_THREADS;

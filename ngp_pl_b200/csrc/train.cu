@@ -60,6 +60,7 @@ __global__ void k_train_compact(const NgpTrainCfg cfg, const float* __restrict__
         int64_t tot = start + n;
         counters[0] = (int)(tot < cfg.max_total_samples ? tot : cfg.max_total_samples);
         counters[1] = 0;
+        counters[4] = 0;
     }
     const float* st = stage_t + (size_t)w * cfg.max_samples;
     const float* sd = stage_dt + (size_t)w * cfg.max_samples;
@@ -119,6 +120,8 @@ static NgpSamples train_samples(const NgpTrainCfg* cfg, const NgpTrainBuffers* b
     s.ray_idx = b->ray_idx; s.ts = b->ts;
     s.n = cfg->max_total_samples;
     s.n_dev = b->counters;
+    s.live_idx = nullptr;
+    s.n_live_dev = nullptr;
     return s;
 }
 
@@ -196,7 +199,8 @@ __global__ void k_train_composite_bw(const NgpTrainCfg cfg, const int* __restric
                                      const float* __restrict__ opacity, const float* __restrict__ depth,
                                      const float* __restrict__ dL_drgb, const float* __restrict__ dL_dopacity,
                                      const float* __restrict__ dL_ddepth, const float* __restrict__ dL_dws,
-                                     float* __restrict__ dsigmas, float* __restrict__ drgbs, float* __restrict__ amax) {
+                                     float* __restrict__ dsigmas, float* __restrict__ drgbs, float* __restrict__ amax,
+                                     int* __restrict__ live_idx, int* __restrict__ counters) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= cfg.n_rays) return;
@@ -221,7 +225,7 @@ __global__ void k_train_composite_bw(const NgpTrainCfg cfg, const int* __restric
     const float dO = dL_dopacity[w] - (dC.x * cfg.bg[0] + dC.y * cfg.bg[1] + dC.z * cfg.bg[2]);
     const float dD = dL_ddepth ? dL_ddepth[w] : 0.f;
     float m = 0.f;
-    composite_ray_warp_bwd(
+    const int n_comp = composite_ray_warp_bwd(
         n, cfg.T_threshold, lane, dO, dD, dC, O, depth[w], C,
         [&](int i) { return __ldg(sg + i); }, [&](int i) { return __ldg(dl + i); }, [&](int i) { return __ldg(tt + i); },
         [&](int i) { return make_float3(__ldg(cl + 3 * i), __ldg(cl + 3 * i + 1), __ldg(cl + 3 * i + 2)); },
@@ -236,9 +240,18 @@ __global__ void k_train_composite_bw(const NgpTrainCfg cfg, const int* __restric
         });
     m = warp_max(m);
     if (lane == 0 && m > 0.f && m < INFINITY) atomicMax(reinterpret_cast<int*>(amax), __float_as_int(m));
+    // the composited samples are the ray's leading n_comp: append them to the list the network backward visits
+    // (every other sample has dsigmas = drgbs = 0 exactly and would only add zeros)
+    if (live_idx) {
+        int at = 0;
+        if (lane == 0) at = atomicAdd(&counters[4], n_comp);
+        at = __shfl_sync(0xffffffffu, at, 0);
+        for (int i = lane; i < n_comp; i += 32) live_idx[at + i] = (int)(start + i);
+    }
 }
 
-__global__ void k_train_grad_scale(float* __restrict__ scalars) {
+__global__ void k_train_grad_scale(float* __restrict__ scalars, int* __restrict__ counters) {
+    counters[5] = counters[4];  // snapshot: counters[4] is cleared by the next step's march
     const float m = scalars[0];
     float s = 1.0f;
     if (m > 0.f && m < INFINITY) {
@@ -262,11 +275,15 @@ extern "C" int ngp_render_train_bwd(const NgpNet* net, const NgpTrainCfg* cfg, c
     const int n = cfg->n_rays;
     k_train_composite_bw<<<ngp_div_up((int64_t)n * 32, 128), 128, 0, st>>>(
         *cfg, b->n_samples, b->offsets, b->sigmas, b->rgbs, b->deltas, b->ts, b->ws, b->rgb, b->opacity, b->depth, dL_drgb,
-        dL_dopacity, dL_ddepth, dL_dws, b->dsigmas, b->drgbs, b->scalars);
+        dL_dopacity, dL_ddepth, dL_dws, b->dsigmas, b->drgbs, b->scalars, b->live_idx, b->counters);
     NGP_CHECK_LAUNCH();
-    k_train_grad_scale<<<1, 1, 0, st>>>(b->scalars);
+    k_train_grad_scale<<<1, 1, 0, st>>>(b->scalars, b->counters);
     NGP_CHECK_LAUNCH();
-    const NgpSamples smp = train_samples(cfg, b);
+    NgpSamples smp = train_samples(cfg, b);
+    if (b->live_idx && b->feat_save) {
+        smp.live_idx = b->live_idx;
+        smp.n_live_dev = b->counters + 4;
+    }
     return ngp_net_backward(net, &smp, b->dsigmas, b->drgbs, b->feat_save, b->scalars + 1, grad_enc, grad_rgb,
                             b->bwd_workspace, b->bwd_workspace_bytes, stream);
 }
@@ -665,7 +682,7 @@ extern "C" int ngp_update_density_grid(const NgpNet* net, float* density_grid, u
         NGP_CHECK_LAUNCH();
         NgpSamples smp;
         smp.xyzs = xyz; smp.dirs = nullptr; smp.rays_o = nullptr; smp.rays_d = nullptr; smp.ray_idx = nullptr; smp.ts = nullptr;
-        smp.n = n_slots; smp.n_dev = nullptr;
+        smp.n = n_slots; smp.n_dev = nullptr; smp.live_idx = nullptr; smp.n_live_dev = nullptr;
         int rc = ngp_net_forward(net, &smp, 0, sigma, nullptr, nullptr, nullptr, stream);
         if (rc) return rc;
         k_grid_scatter<<<ngp_div_up(n_slots, 256), 256, 0, st>>>(cell_idx, sigma, n_slots, tmp + c * g3);

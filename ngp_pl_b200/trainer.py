@@ -52,7 +52,7 @@ class Trainer:
     def __init__(self, model: NGP, n_rays=8192, lr=1e-2, exp_step_factor=0.0, bg=(1.0, 1.0, 1.0), lambda_opacity=1e-3,
                  T_threshold=1e-4, betas=(0.9, 0.999), eps=1e-15, max_total_samples=None, update_interval=16,
                  warmup_steps=256, process_group=None, world_size=1, rank=0, seed=0, materialize_ws=False, ddp="nccl",
-                 lambda_distortion=0.0):
+                 lambda_distortion=0.0, skip_dead_samples=True):
         self.model = model
         dev = model.density_bitfield.device
         if dev.type != "cuda":
@@ -152,7 +152,7 @@ class Trainer:
             self.stage_dt = torch.empty(N * MAX_SAMPLES, **f32)
             self.n_samples = torch.zeros(N, **i32)
             self.offsets = torch.zeros(N, **i32)
-            self.counters = torch.zeros(4, **i32)
+            self.counters = torch.zeros(8, **i32)
             self.rgb = torch.zeros(N, 3, **f32)
             self.opacity = torch.zeros(N, **f32)
             self.depth = torch.zeros(N, **f32)
@@ -164,6 +164,8 @@ class Trainer:
             self.ws = torch.empty(cap, **f32) if materialize_ws else None
             self.dsigmas = torch.empty(cap, **f32)
             self.drgbs = torch.empty(cap, 3, **f32)
+            # samples past a ray's termination get exactly zero gradient: the backward visits only the others
+            self.live_idx = torch.empty(cap, **i32) if skip_dead_samples else None
             self.feat_save = torch.empty(feat_save_bytes(cap), device=dev, dtype=torch.uint8)
             self.scalars = torch.zeros(8, **f32)
             self.dL_drgb = torch.zeros(N, 3, **f32)
@@ -185,6 +187,7 @@ class Trainer:
                          "scalars", "scan_temp"):
                 setattr(b, name, getattr(self, name).data_ptr())
             b.ws = self.ws.data_ptr() if self.ws is not None else None
+            b.live_idx = self.live_idx.data_ptr() if self.live_idx is not None else None
             b.density_bitfield = model.density_bitfield.data_ptr()
             b.scan_temp_bytes = scan_bytes
             bwd_bytes = L.ngp_net_backward_workspace(cap)
@@ -417,7 +420,7 @@ class Trainer:
         n = self.n_rays
         mse = s[2] / (3 * n)
         loss = mse + self.cfg.lambda_opacity * s[3] / n
-        out = dict(rm_samples=c[2], vr_samples=c[3], mse=mse, psnr=-10 * math.log10(max(mse, 1e-12)))
+        out = dict(rm_samples=c[2], vr_samples=c[3], bw_samples=c[5] if self.live_idx is not None else c[2], mse=mse, psnr=-10 * math.log10(max(mse, 1e-12)))
         if self.lambda_distortion > 0:
             out["distortion"] = self.lambda_distortion * float(self.dist_loss.mean())
             loss += out["distortion"]

@@ -26,7 +26,7 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert hasattr(lib, s), "libngp_b200.so does not export " + s
     assert sorted(_lib.SIGNATURES.keys()) == syms, (
         "ctypes table and header disagree: %s" % (set(_lib.SIGNATURES.keys()) ^ set(syms)))
-    assert lib.ngp_abi_version() == 1
+    assert lib.ngp_abi_version() == _lib.ABI_VERSION
 
 
 def test_header_is_plain_c():

@@ -302,3 +302,53 @@ def test_fused_trainer_with_distortion_loss_matches_autograd():
     g_ref = torch.cat([model.xyz_encoder.params.grad, model.rgb_net.params.grad])
     s = g_ref.abs().max().item()
     assert (g_ref - tr.G).abs().max().item() < 3e-3 * s
+
+
+def test_backward_visits_only_composited_samples():
+    """The samples after a ray's terminating sample get exactly zero gradient (composite_train_bw,
+    volumerendering.cu:87-151): the fused backward skips them through the live list. Same gradients as
+    the backward over every marched sample."""
+    import ctypes as C
+    from ngp_pl_b200 import synth, _lib
+    from ngp_pl_b200.models.networks import NGP
+    from ngp_pl_b200.trainer import Trainer
+    scene = synth.lego_scene(0)
+    # a briefly trained model: opaque surfaces, so most rays terminate well before their last marched sample
+    K = synth.intrinsics(W=200, H=200, fx=1111.11 / 4)
+    bank = synth.RayBank(scene, n_images=40, K=K, device="cuda")
+    model = NGP(scene.scale).cuda()
+    tr0 = Trainer(model, n_rays=4096, lr=1e-2)
+    tr0.attach_bank(bank)
+    for _ in range(300):
+        tr0.train_step()
+    tr0.gather_master_params()
+    torch.cuda.synchronize()
+    n = 4096
+    o, d, gt = bank.sample(n)
+    noise = torch.rand(n, device="cuda", generator=torch.Generator("cuda").manual_seed(2))
+    out = {}
+    for skip in (True, False):
+        tr = Trainer(model, n_rays=n, skip_dead_samples=skip)
+        tr.set_batch(o, d, gt)
+        tr.noise.copy_(noise)
+        _lib.check(_lib.lib().ngp_render_train_fwd(C.byref(tr.net), C.byref(tr.cfg), C.byref(tr.buf), tr._st()), "fwd")
+        tr.loss_backward()
+        torch.cuda.synchronize()
+        out[skip] = (tr.G.clone(), tr.stats(), tr)
+    st = out[True][1]
+    assert st["rm_samples"] == out[False][1]["rm_samples"] and st["vr_samples"] == out[False][1]["vr_samples"]
+    # live list = composited samples = vr_samples + one terminating sample per terminated ray
+    assert st["vr_samples"] <= st["bw_samples"] <= st["vr_samples"] + n
+    assert st["bw_samples"] < 0.9 * st["rm_samples"], st
+    assert out[False][1]["bw_samples"] == st["rm_samples"]
+    tr = out[True][2]
+    live = tr.live_idx[:st["bw_samples"]].long()
+    assert live.unique().numel() == live.numel()
+    dead = torch.ones(st["rm_samples"], dtype=torch.bool, device="cuda")
+    dead[live] = False
+    assert tr.dsigmas[:st["rm_samples"]][dead].abs().max().item() == 0
+    assert tr.drgbs[:st["rm_samples"]][dead].abs().max().item() == 0
+    g1, g0 = out[True][0], out[False][0]
+    s = g0.abs().max().item()
+    assert s > 0
+    assert (g1 - g0).abs().max().item() < 2e-4 * s  # fp32 atomics re-associate; fp16 operands are identical
