@@ -221,7 +221,8 @@ typedef struct {
     int32_t* offsets;             /* (n_rays) exclusive prefix sum == rays_a[:,1] */
     int32_t* counters;            /* int32[8]: [0] marched samples (rm_samples), [1] composited (vr_samples) of the step in flight;
                                      [2],[3] the same, snapshotted by ngp_nerf_loss_grad for the last completed step;
-                                     [4] length of live_idx (written by the backward), [5] its snapshot, [6..7] reserved */
+                                     [4] append cursor of live_idx while the compositing backward runs (0 otherwise), [5] length of live_idx,
+                                     [6..7] free for the caller (the Trainer keeps its ngp_sample_rays draw counter there) */
     float* rgb;                   /* (n_rays,3) composited colour incl. background */
     float* opacity;               /* (n_rays) */
     float* depth;                 /* (n_rays) */
@@ -291,6 +292,14 @@ int ngp_adam_step_p2p(int world, int rank, const uint64_t* peer_grads, float* pa
 int ngp_gen_rays(const int64_t* img_idx, const int64_t* pix_idx, const float* poses /* (n_img,3,4) */,
                  const float* directions /* (n_pix,3) */, const uint8_t* images /* (n_img,n_pix,3) or NULL */,
                  int64_t n_pix, int n, float* rays_o, float* rays_d, float* rgb_gt, void* stream);
+
+/* The same with the random draw on the device, in one kernel: every ray gets a uniform (image, pixel) pair with
+ * replacement (reference datasets/base.py:22-30, ray sampling strategy 'all_images') and its start jitter noise[i] in [0,1)
+ * (reference custom_functions.py:84) from Philox-4x32-10 keyed by (seed, stream_id) with counter (ray, draw); rng_draw is a
+ * device int32[2] {draw counter, scratch 0}, advanced by the kernel, so CUDA-graph replays draw fresh batches. */
+int ngp_sample_rays(const float* poses, const float* directions, const uint8_t* images, int n_img, int64_t n_pix, int n,
+                    uint32_t seed, uint32_t stream_id, int32_t* rng_draw, float* rays_o, float* rays_d, float* rgb_gt,
+                    float* noise, void* stream);
 
 /* Occupancy-grid refresh on the device (reference networks.py:240-269 + :169-195), no host sync:
  * picks cells (all cells when warmup, else M uniform + M occupied per cascade), evaluates sigma at a

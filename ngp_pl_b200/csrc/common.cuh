@@ -63,6 +63,35 @@ __device__ __forceinline__ float warp_scan_mul(float v, int lane) {
     return v;
 }
 
+// L2 eviction-priority hints. The optimiser streams ~400 MB (params, moments, gradients) through the 126 MB L2 once per
+// step; without hints that evicts the fp16 hash table (24 MB), the zeroed gradient table (49 MB) and the occupancy
+// bitfield which the next step's kernels gather from / reduce into, and those kernels then run from DRAM.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float4 ld_f4_hint(const float4* ptr, uint64_t policy) {
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(ptr), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ void st_f4_hint(float4* ptr, float4 v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w),
+                 "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ void st_u2_hint(uint2* ptr, uint2 v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v2.u32 [%0], {%1,%2}, %3;" ::"l"(ptr), "r"(v.x), "r"(v.y), "l"(policy) : "memory");
+}
+
 // 8-byte vector reduction (two fp32 adds in one L2 atomic transaction; sm_90+)
 __device__ __forceinline__ void red_add_f32x2(float* addr, float a, float b) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");

@@ -235,10 +235,27 @@ __device__ __forceinline__ int march_ray_warp(const MarchRay& ray, const MarchCo
     while (alive) {
         // 1. 32 consecutive chain points: lane j holds c_j
         float p = t;
+        bool chain_done = false;
+        if (CONST_DT) {
+            // Inside one binade every rounded add of the constant step moves t by the same multiple of its ulp, so the
+            // chain is t + j*inc with inc = fl(t + dt) - t (exact). Guess that, then CHECK the defining recurrence
+            // c_j == fl(c_{j-1} + dt) in every lane; any mismatch (binade crossing, a tie) takes the serial adds below,
+            // so the values are the serial ones bit for bit either way.
+            const float inc = __fadd_rn(__fadd_rn(t, c.dt_lo), -t);
+            const float guess = __fmaf_rn((float)lane, inc, t);
+            const float prev = __shfl_up_sync(0xffffffffu, guess, 1);
+            const bool ok = lane == 0 || __fadd_rn(prev, c.dt_lo) == guess;
+            if (__all_sync(0xffffffffu, ok)) {
+                p = guess;
+                chain_done = true;
+            }
+        }
+        if (!chain_done) {
 #pragma unroll
-        for (int j = 0; j < 31; ++j) {
-            const float nx = __fadd_rn(p, CONST_DT ? c.dt_lo : march_dt(p, c));
-            if (lane > j) p = nx;
+            for (int j = 0; j < 31; ++j) {
+                const float nx = __fadd_rn(p, CONST_DT ? c.dt_lo : march_dt(p, c));
+                if (lane > j) p = nx;
+            }
         }
         float t_next = __fadd_rn(p, CONST_DT ? c.dt_lo : march_dt(p, c));
         t_next = __shfl_sync(0xffffffffu, t_next, 31);
@@ -247,7 +264,24 @@ __device__ __forceinline__ int march_ray_warp(const MarchRay& ray, const MarchCo
         const MarchProbe pr = march_probe<ONE_CASCADE>(ray, c, p);
         const unsigned valid_mask = __ballot_sync(0xffffffffu, valid);
         const unsigned occ_mask = __ballot_sync(0xffffffffu, valid && pr.occ);
-        // 3. which of them does the serial walk visit?
+        // 3. which of them does the serial walk visit? An empty visit at lane j jumps to the first chain point that is not
+        // below its t_target: every lane finds that successor for its own point with a binary search over the (increasing)
+        // chain values, so the walk below costs one shuffle per empty visit.
+        int nxt;
+        {
+            int lo = lane + 1, hi = 32;
+#pragma unroll
+            for (int it = 0; it < 5; ++it) {
+                const int mid = (lo + hi) >> 1;
+                const float pm = __shfl_sync(0xffffffffu, p, mid & 31);
+                const bool ge = mid < 32 && !(pm < pr.t_target);
+                if (lo < hi) {
+                    if (ge) hi = mid;
+                    else lo = mid + 1;
+                }
+            }
+            nxt = lo;
+        }
         int cur = 0;
         if (pending) {
             const unsigned m = __ballot_sync(0xffffffffu, !(p < skip_to));
@@ -277,16 +311,12 @@ __device__ __forceinline__ int march_ray_warp(const MarchRay& ray, const MarchCo
                 cur += run;
             } else {
                 // empty cell: jump to the first chain point that is not below t_target
-                const float tt = __shfl_sync(0xffffffffu, pr.t_target, cur);
-                const unsigned above = cur >= 31 ? 0u : (0xffffffffu << (cur + 1));
-                const unsigned m = __ballot_sync(0xffffffffu, !(p < tt)) & above;
-                if (m) {
-                    cur = __ffs(m) - 1;
-                } else {
-                    cur = 32;
+                const int to = __shfl_sync(0xffffffffu, nxt, cur);
+                if (to >= 32) {  // past this block of 32: carry the target over
                     pending = true;
-                    skip_to = tt;
+                    skip_to = __shfl_sync(0xffffffffu, pr.t_target, cur);
                 }
+                cur = to;
             }
         }
         if ((sample_mask >> lane) & 1u) emit(n + __popc(sample_mask & ((1u << lane) - 1u)), p, pr.dt);

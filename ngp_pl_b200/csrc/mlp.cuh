@@ -110,9 +110,21 @@ struct MlpWeightsBwd {
     __half w3rT[64 * LD16];
 };
 
+// Row-major [rows][cols] global matrix -> padded shared rows, 16 bytes per cp.async (cols % 8 == 0, ld % 8 == 0, both
+// bases 16-B aligned). The copies are asynchronous: call cp_async_wait_all() (+ __syncthreads()) before reading.
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
 __device__ __forceinline__ void load_matrix(__half* dst, int ld, const __half* __restrict__ src, int rows, int cols,
                                             int tid, int nthreads) {
-    for (int i = tid; i < rows * cols; i += nthreads) dst[(i / cols) * ld + (i % cols)] = src[i];
+    const int cpr = cols >> 3;  // 16-byte chunks per row
+    for (int i = tid; i < rows * cpr; i += nthreads) {
+        const int r = i / cpr, c = i - r * cpr;
+        cp_async_16(dst + r * ld + 8 * c, src + r * cols + 8 * c);
+    }
 }
 __device__ __forceinline__ void load_matrix_T(__half* dst, int ld, const __half* __restrict__ src, int rows, int cols,
                                               int tid, int nthreads) {
@@ -128,6 +140,7 @@ __device__ __forceinline__ void load_weights_fwd(MlpWeightsFwd& s, const __half*
         load_matrix(s.w2r, LD64, wr + 2048, 64, 64, tid, nthreads);
         load_matrix(s.w3r, LD64, wr + 2048 + 4096, 16, 64, tid, nthreads);
     }
+    cp_async_wait_all();
 }
 __device__ __forceinline__ void load_weights_bwd(MlpWeightsBwd& s, const __half* __restrict__ wd, const __half* __restrict__ wr,
                                                  int tid, int nthreads) {

@@ -98,11 +98,12 @@ __device__ __forceinline__ void load_rgb_weights(RgbW& s, const __half* __restri
     load_matrix(s.w1r, LD32, wr, 64, 32, tid, nthreads);
     load_matrix(s.w2r, LD64, wr + 2048, 64, 64, tid, nthreads);
     load_matrix(s.w3r, LD64, wr + 2048 + 4096, 16, 64, tid, nthreads);
+    cp_async_wait_all();
 }
 
 __global__ void __launch_bounds__(MOD_THREADS)
 k_mlp_rgb_fwd(const __half* __restrict__ wr, const __half* __restrict__ X, int64_t n, int act, __half* __restrict__ out3) {
-    __shared__ RgbW sw;
+    __shared__ __align__(16) RgbW sw;
     load_rgb_weights(sw, wr, threadIdx.x, MOD_THREADS);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
@@ -321,6 +322,7 @@ k_enc_bwd(const __half* __restrict__ wd, const uint4* __restrict__ feat_save, co
     EncBwdSmem& S = *reinterpret_cast<EncBwdSmem*>(smem_raw);
     load_matrix(S.w1d, LD32, wd, 64, 32, threadIdx.x, MOD_THREADS);
     load_matrix(S.w2d, LD64, wd + 2048, 16, 64, threadIdx.x, MOD_THREADS);
+    cp_async_wait_all();
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
     const int64_t n_mtiles = (n + 15) / 16;

@@ -69,6 +69,49 @@ extern "C" int ngp_cast_params(const float* src, uint16_t* dst_half, int64_t n, 
 }
 
 // -------------------------------------------------------------------------------------------------
+// Dynamic tile scheduling for the persistent kernels: warps (forward) / CTAs (backward) take the next tile from a
+// device counter instead of striding, so a CTA that becomes resident late -- the trainer runs the next step's
+// march on a second stream under these kernels -- simply takes fewer tiles instead of stretching the kernel by a
+// whole extra wave. A slot is {next tile, finished CTAs}; the last CTA to finish re-arms it. Slots rotate per
+// launch, so launches that may overlap on different streams never share one.
+// -------------------------------------------------------------------------------------------------
+#define NGP_SCHED_EAGER 1024  // rotated by eager launches (a collision needs two launches 1024 apart to overlap in time)
+#define NGP_SCHED_GRAPH 1024  // handed out once each to launches recorded into CUDA graphs (their slot is baked in)
+__device__ int g_sched[NGP_SCHED_EAGER + NGP_SCHED_GRAPH][2];
+// nullptr => the kernel falls back to static striding (graph slots exhausted)
+static int* sched_slot(cudaStream_t st) {
+    static int* bases[64] = {nullptr};  // per device: a __device__ symbol has one address per device
+    static unsigned eager_seq = 0, graph_seq = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!bases[dev]) {
+        void* p = nullptr;
+        if (cudaGetSymbolAddress(&p, g_sched) != cudaSuccess) return nullptr;
+        bases[dev] = (int*)p;
+    }
+    int* base = bases[dev];
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) return nullptr;
+    if (cs != cudaStreamCaptureStatusNone) {
+        if (graph_seq >= NGP_SCHED_GRAPH) return nullptr;
+        return base + 2 * (size_t)(NGP_SCHED_EAGER + graph_seq++);
+    }
+    return base + 2 * (size_t)(eager_seq++ % NGP_SCHED_EAGER);
+}
+__device__ __forceinline__ void sched_finish(int* sched) {
+    if (!sched) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&sched[1], 1) == (int)gridDim.x - 1) {  // every CTA is past its last grab
+            sched[0] = 0;
+            sched[1] = 0;
+            __threadfence();
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
 // sample access
 // -------------------------------------------------------------------------------------------------
 struct SampleIn {
@@ -170,20 +213,25 @@ __device__ __forceinline__ float hi_half(uint32_t u) { return __half2float(__ush
 template <int FWD_MT, int FWD_THREADS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(FWD_THREADS, MIN_BLOCKS)
 k_ngp_fwd(const NgpNet net, const NgpSamples smp, const int want_rgb, float* __restrict__ sigmas, float* __restrict__ rgbs,
-          __half* __restrict__ h_out, uint4* __restrict__ feat_save) {
-    __shared__ MlpWeightsFwd sw;
+          __half* __restrict__ h_out, uint4* __restrict__ feat_save, int* __restrict__ sched) {
+    __shared__ __align__(16) MlpWeightsFwd sw;
     const __half* wd = reinterpret_cast<const __half*>(net.enc_params_h);
     const __half* wr = want_rgb ? reinterpret_cast<const __half*>(net.rgb_params_h) : nullptr;
     load_weights_fwd(sw, wd, wr, threadIdx.x, FWD_THREADS);
     __syncthreads();
     const uint32_t* table = reinterpret_cast<const uint32_t*>(wd + NGP_DENSITY_MLP_PARAMS);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
     const int64_t n = sample_count(smp);
     const int64_t n_tiles = (n + 16 * FWD_MT - 1) / (16 * FWD_MT);
-    const int warps_per_cta = FWD_THREADS / 32;
-
-    for (int64_t tile = (int64_t)blockIdx.x * warps_per_cta + warp; tile < n_tiles; tile += (int64_t)gridDim.x * warps_per_cta) {
+    const int n_warps = (int)gridDim.x * (FWD_THREADS / 32);
+    int grabbed = (int)blockIdx.x * (FWD_THREADS / 32) + (threadIdx.x >> 5);  // static striding when there is no slot
+    if (sched && lane == 0) grabbed = atomicAdd(&sched[0], 1);
+    for (;;) {
+        const int64_t tile = __shfl_sync(0xffffffffu, grabbed, 0);
+        if (tile >= n_tiles) break;
+        if (!sched) grabbed += n_warps;
+        else if (lane == 0) grabbed = atomicAdd(&sched[0], 1);  // the next ticket travels while this tile is computed
         const int64_t base = tile * 16 * FWD_MT;
         SampleIn sm[FWD_MT][2];
         bool valid[FWD_MT][2];
@@ -284,6 +332,7 @@ k_ngp_fwd(const NgpNet net, const NgpSamples smp, const int want_rgb, float* __r
                 }
             }
     }
+    sched_finish(sched);
 }
 
 template <int MT, int THREADS, int MIN_BLOCKS>
@@ -293,8 +342,9 @@ static int launch_fwd(const NgpNet* net, const NgpSamples* smp, int want_rgb, fl
     const int64_t want = (n_tiles + THREADS / 32 - 1) / (THREADS / 32);
     const int64_t cap = (int64_t)ngp_sm_count() * MIN_BLOCKS;
     const int grid = (int)(want < cap ? want : cap);
+    int* sched = sched_slot(st);
     k_ngp_fwd<MT, THREADS, MIN_BLOCKS><<<grid, THREADS, 0, st>>>(*net, *smp, want_rgb, sigmas, rgbs, (__half*)h_out,
-                                                                 (uint4*)feat_save);
+                                                                 (uint4*)feat_save, sched);
     return 0;
 }
 
@@ -677,9 +727,10 @@ __device__ __forceinline__ void wgrad_tile2x2(float (&acc0)[4], float (&acc1)[4]
 __global__ void __launch_bounds__(B2_THREADS, 1)
 k_ngp_bwd2(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_dsigmas, const float* __restrict__ dL_drgbs,
            const uint4* __restrict__ feat_save, const float* __restrict__ loss_scale, float* __restrict__ grad_enc,
-           float* __restrict__ grad_rgb, uint32_t* __restrict__ dfeat, const int64_t dfeat_stride) {
+           float* __restrict__ grad_rgb, uint32_t* __restrict__ dfeat, const int64_t dfeat_stride, int* __restrict__ sched) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Bwd2Smem& S = *reinterpret_cast<Bwd2Smem*>(smem_raw);
+    __shared__ int s_blk[2];  // tickets of the current and the next block of 256 rows (double-buffered)
     const __half* wd = reinterpret_cast<const __half*>(net.enc_params_h);
     const __half* wr = reinterpret_cast<const __half*>(net.rgb_params_h);
     load_weights_fwd(S.wf, wd, wr, threadIdx.x, B2_THREADS);
@@ -701,7 +752,13 @@ k_ngp_bwd2(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
 
-    for (int64_t blk = blockIdx.x; blk < n_blks; blk += gridDim.x) {
+    if (threadIdx.x == 0) s_blk[0] = sched ? atomicAdd(&sched[0], 1) : (int)blockIdx.x;
+    __syncthreads();
+    for (int it = 0;; ++it) {
+        const int64_t blk = s_blk[it & 1];
+        if (blk >= n_blks) break;
+        // ticket of the next block: written to the other slot, published by this iteration's barriers
+        if (threadIdx.x == 0) s_blk[(it + 1) & 1] = sched ? atomicAdd(&sched[0], 1) : (int)(blk + gridDim.x);
         const int64_t mtile = blk * B2_WARPS + warp;
         const int64_t base = mtile * 16;
         bool valid[2];
@@ -898,6 +955,7 @@ k_ngp_bwd2(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_
         }
     }
 
+    sched_finish(sched);
     // ---- flush the weight-gradient tiles ----
     if (warp < 8) wgrad_flush(acc[0], grad_rgb + 2048 + 4096, 64, 0, warp, inv_scale, g, q);  // W3r
     else wgrad_flush(acc[0], grad_enc + 2048, 64, 0, warp - 8, inv_scale, g, q);              // W2d
@@ -1031,9 +1089,10 @@ extern "C" int ngp_net_backward_mlp(const NgpNet* net, const NgpSamples* smp, co
     } else {
         const int64_t n_blks = (n_mtiles + B2_WARPS - 1) / B2_WARPS;
         const int grid = (int)(n_blks < (int64_t)ngp_sm_count() ? n_blks : ngp_sm_count());
+        int* sched = sched_slot((cudaStream_t)stream);
         k_ngp_bwd2<<<grid, B2_THREADS, sizeof(Bwd2Smem), (cudaStream_t)stream>>>(
             *net, *smp, dL_dsigmas, dL_drgbs, (const uint4*)feat_save, loss_scale, grad_enc, grad_rgb, (uint32_t*)workspace,
-            n_mtiles * 16);
+            n_mtiles * 16, sched);
     }
     NGP_CHECK_LAUNCH();
     return 0;

@@ -137,6 +137,30 @@ static int check_train_args(const NgpNet* net, const NgpTrainCfg* cfg, const Ngp
     return 0;
 }
 
+// exclusive prefix sum of up to 1024*SCAN1_ITEMS per-ray counts by ONE block (the training batch is 8192 rays: a
+// device-wide scan would cost two launches for 32 KB of data)
+#define SCAN1_ITEMS 16
+__global__ void __launch_bounds__(1024) k_scan_one_block(const int* __restrict__ in, int* __restrict__ out, int n) {
+    typedef cub::BlockScan<int, 1024> BlockScan;
+    __shared__ typename BlockScan::TempStorage temp;
+    const int per = (n + 1023) / 1024;  // <= SCAN1_ITEMS consecutive items per thread
+    const int first = threadIdx.x * per;
+    int v[SCAN1_ITEMS];
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN1_ITEMS; ++k) {
+        v[k] = (k < per && first + k < n) ? in[first + k] : 0;
+        sum += v[k];
+    }
+    int base;
+    BlockScan(temp).ExclusiveSum(sum, base);
+#pragma unroll
+    for (int k = 0; k < SCAN1_ITEMS; ++k) {
+        if (k < per && first + k < n) out[first + k] = base;
+        base += v[k];
+    }
+}
+
 // first half of the forward: AABB + march + prefix sum + compaction. Depends only on the rays, the jitter
 // and the occupancy bitfield (NOT on the network weights), so a trainer may run it for step i+1 while the
 // optimiser of step i is still updating the weights.
@@ -159,8 +183,13 @@ extern "C" int ngp_render_train_march(const NgpTrainCfg* cfg, const NgpTrainBuff
     else NGP_LAUNCH_MARCH(false, false);
 #undef NGP_LAUNCH_MARCH
     NGP_CHECK_LAUNCH();
-    size_t temp_bytes = b->scan_temp_bytes;
-    NGP_CUDA(cub::DeviceScan::ExclusiveSum(b->scan_temp, temp_bytes, b->n_samples, b->offsets, n, st));
+    if (n <= 1024 * SCAN1_ITEMS) {
+        k_scan_one_block<<<1, 1024, 0, st>>>(b->n_samples, b->offsets, n);
+        NGP_CHECK_LAUNCH();
+    } else {
+        size_t temp_bytes = b->scan_temp_bytes;
+        NGP_CUDA(cub::DeviceScan::ExclusiveSum(b->scan_temp, temp_bytes, b->n_samples, b->offsets, n, st));
+    }
     k_train_compact<<<ngp_div_up((int64_t)n * 32, 256), 256, 0, st>>>(*cfg, b->stage_t, b->stage_dt, b->n_samples, b->offsets,
                                                                        b->ray_idx, b->ts, b->deltas, b->counters);
     NGP_CHECK_LAUNCH();
@@ -251,7 +280,10 @@ __global__ void k_train_composite_bw(const NgpTrainCfg cfg, const int* __restric
 }
 
 __global__ void k_train_grad_scale(float* __restrict__ scalars, int* __restrict__ counters) {
-    counters[5] = counters[4];  // snapshot: counters[4] is cleared by the next step's march
+    // the live list is complete: publish its length and re-arm the append counter, so that counters[4] is zero
+    // whenever a compositing backward starts, whatever the caller's order of calls
+    counters[5] = counters[4];
+    counters[4] = 0;
     const float m = scalars[0];
     float s = 1.0f;
     if (m > 0.f && m < INFINITY) {
@@ -282,7 +314,7 @@ extern "C" int ngp_render_train_bwd(const NgpNet* net, const NgpTrainCfg* cfg, c
     NgpSamples smp = train_samples(cfg, b);
     if (b->live_idx && b->feat_save) {
         smp.live_idx = b->live_idx;
-        smp.n_live_dev = b->counters + 4;
+        smp.n_live_dev = b->counters + 5;
     }
     return ngp_net_backward(net, &smp, b->dsigmas, b->drgbs, b->feat_save, b->scalars + 1, grad_enc, grad_rgb,
                             b->bwd_workspace, b->bwd_workspace_bytes, stream);
@@ -345,11 +377,14 @@ __global__ void k_adam(float* __restrict__ p, float* __restrict__ g, float* __re
     const float step_size = lr / bc1;
     const float inv_sqrt_bc2 = rsqrtf(bc2);
     const int64_t n4 = n >> 2;
+    // fp32 params, moments and the consumed gradients stream through L2 (evict first); the fp16 working copy the
+    // forward gathers from is kept (evict last); the zeroed gradients (next step's reduction target) stay normal
+    const uint64_t stream_pol = l2_policy_evict_first(), keep_pol = l2_policy_evict_last();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-        float4 pv = reinterpret_cast<float4*>(p)[i];
-        float4 gv = reinterpret_cast<float4*>(g)[i];
-        float4 mv = reinterpret_cast<float4*>(m)[i];
-        float4 vv = reinterpret_cast<float4*>(v)[i];
+        float4 pv = ld_f4_hint(reinterpret_cast<const float4*>(p) + i, stream_pol);
+        float4 gv = ld_f4_hint(reinterpret_cast<const float4*>(g) + i, stream_pol);
+        float4 mv = ld_f4_hint(reinterpret_cast<const float4*>(m) + i, stream_pol);
+        float4 vv = ld_f4_hint(reinterpret_cast<const float4*>(v) + i, stream_pol);
         float* pp = &pv.x; float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -359,15 +394,15 @@ __global__ void k_adam(float* __restrict__ p, float* __restrict__ g, float* __re
             const float denom = sqrtf(vp[k]) * inv_sqrt_bc2 + eps;
             pp[k] -= step_size * (mp[k] / denom);
         }
-        reinterpret_cast<float4*>(p)[i] = pv;
-        reinterpret_cast<float4*>(m)[i] = mv;
-        reinterpret_cast<float4*>(v)[i] = vv;
+        st_f4_hint(reinterpret_cast<float4*>(p) + i, pv, stream_pol);
+        st_f4_hint(reinterpret_cast<float4*>(m) + i, mv, stream_pol);
+        st_f4_hint(reinterpret_cast<float4*>(v) + i, vv, stream_pol);
         reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ph) {
             uint2 h;
             h.x = pack_half2(pv.x, pv.y);
             h.y = pack_half2(pv.z, pv.w);
-            reinterpret_cast<uint2*>(ph)[i] = h;
+            st_u2_hint(reinterpret_cast<uint2*>(ph) + i, h, keep_pol);
         }
     }
     // tail
@@ -431,6 +466,7 @@ __global__ void k_adam_p2p(const PeerPtrs peers, const int world, float* __restr
     const float bc2 = 1.0f - powf(beta2, (float)t);
     const float step_size = lr / bc1;
     const float inv_sqrt_bc2 = rsqrtf(bc2);
+    const uint64_t stream_pol = l2_policy_evict_first();
     for (int64_t i = lo4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < hi4; i += (int64_t)gridDim.x * blockDim.x) {
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
         float4 part[NGP_MAX_PEERS];
@@ -440,9 +476,9 @@ __global__ void k_adam_p2p(const PeerPtrs peers, const int world, float* __restr
 #pragma unroll
         for (int r = 0; r < NGP_MAX_PEERS; ++r)
             if (r < world) { g.x += part[r].x; g.y += part[r].y; g.z += part[r].z; g.w += part[r].w; }
-        float4 pv = reinterpret_cast<float4*>(p)[i];
-        float4 mv = reinterpret_cast<float4*>(m)[i];
-        float4 vv = reinterpret_cast<float4*>(v)[i];
+        float4 pv = ld_f4_hint(reinterpret_cast<const float4*>(p) + i, stream_pol);
+        float4 mv = ld_f4_hint(reinterpret_cast<const float4*>(m) + i, stream_pol);
+        float4 vv = ld_f4_hint(reinterpret_cast<const float4*>(v) + i, stream_pol);
         float* pp = &pv.x; float* gp = &g.x; float* mp = &mv.x; float* vp = &vv.x;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -451,9 +487,9 @@ __global__ void k_adam_p2p(const PeerPtrs peers, const int world, float* __restr
             vp[k] = beta2 * vp[k] + (1.0f - beta2) * gr * gr;
             pp[k] -= step_size * (mp[k] / (sqrtf(vp[k]) * inv_sqrt_bc2 + eps));
         }
-        reinterpret_cast<float4*>(p)[i] = pv;
-        reinterpret_cast<float4*>(m)[i] = mv;
-        reinterpret_cast<float4*>(v)[i] = vv;
+        st_f4_hint(reinterpret_cast<float4*>(p) + i, pv, stream_pol);
+        st_f4_hint(reinterpret_cast<float4*>(m) + i, mv, stream_pol);
+        st_f4_hint(reinterpret_cast<float4*>(v) + i, vv, stream_pol);
         uint2 h;
         h.x = pack_half2(pv.x, pv.y);
         h.y = pack_half2(pv.z, pv.w);
@@ -530,6 +566,69 @@ extern "C" int ngp_gen_rays(const int64_t* img_idx, const int64_t* pix_idx, cons
     if (n == 0) return 0;
     k_gen_rays<<<ngp_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(img_idx, pix_idx, poses, directions, images, n_pix, n,
                                                                       rays_o, rays_d, rgb_gt);
+    NGP_CHECK_LAUNCH();
+    return 0;
+}
+
+// Batch assembly in ONE kernel: draws the (image, pixel) pair of every ray and its start jitter from a counter-based
+// generator (Philox-4x32-10 keyed by (seed, stream), counter = (draw, ray)) and builds the ray as k_gen_rays does.
+// `draw` lives on the device (rng_draw[0], advanced by the kernel's last block), so a CUDA-graph replay draws a new batch.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+
+__global__ void k_sample_rays(const float* __restrict__ poses, const float* __restrict__ directions,
+                              const uint8_t* __restrict__ images, uint32_t n_img, uint32_t n_pix, int n, uint32_t seed,
+                              uint32_t stream_id, int* __restrict__ rng_draw, float* __restrict__ rays_o,
+                              float* __restrict__ rays_d, float* __restrict__ rgb_gt, float* __restrict__ noise) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t draw = (uint32_t)rng_draw[0];
+    if (i < n) {
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)i, draw, 0u, 0u), make_uint2(seed, stream_id));
+        // uniform integers by multiply-high (bias < n/2^32), like torch's random_(0, n) up to the generator
+        const uint32_t im = __umulhi(r.x, n_img), px = __umulhi(r.y, n_pix);
+        noise[i] = (float)(r.z >> 8) * (1.0f / 16777216.0f);
+        const float* P = poses + 12 * (size_t)im;
+        const float dx = directions[3 * (size_t)px], dy = directions[3 * (size_t)px + 1], dz = directions[3 * (size_t)px + 2];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            rays_d[3 * i + k] = fmaf(dz, P[4 * k + 2], fmaf(dy, P[4 * k + 1], dx * P[4 * k]));
+            rays_o[3 * i + k] = P[4 * k + 3];
+        }
+        const uint8_t* c = images + 3 * ((size_t)im * n_pix + px);
+        rgb_gt[3 * i] = c[0] * (1.0f / 255.0f);
+        rgb_gt[3 * i + 1] = c[1] * (1.0f / 255.0f);
+        rgb_gt[3 * i + 2] = c[2] * (1.0f / 255.0f);
+    }
+    // the last block to finish advances the draw counter (every block has read it by then)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&rng_draw[1], 1) == (int)gridDim.x - 1) {
+            rng_draw[1] = 0;
+            rng_draw[0] = (int)(draw + 1u);
+        }
+    }
+}
+
+extern "C" int ngp_sample_rays(const float* poses, const float* directions, const uint8_t* images, int n_img, int64_t n_pix,
+                               int n, uint32_t seed, uint32_t stream_id, int32_t* rng_draw, float* rays_o, float* rays_d,
+                               float* rgb_gt, float* noise, void* stream) {
+    if (n < 0 || n_img < 1 || n_pix < 1 || n_pix > 0xffffffffll || !poses || !directions || !images || !rng_draw || !rays_o ||
+        !rays_d || !rgb_gt || !noise)
+        return NGP_EINVAL;
+    if (n == 0) return 0;
+    k_sample_rays<<<ngp_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(poses, directions, images, (uint32_t)n_img,
+                                                                         (uint32_t)n_pix, n, seed, stream_id, rng_draw, rays_o,
+                                                                         rays_d, rgb_gt, noise);
     NGP_CHECK_LAUNCH();
     return 0;
 }

@@ -48,6 +48,9 @@ def shard_range(n_items, world_size, rank):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+_SET_FIELDS = ("rays_o", "rays_d", "rgb_gt", "noise", "n_samples", "offsets", "counters", "ray_idx", "ts", "deltas")
+
+
 class Trainer:
     def __init__(self, model: NGP, n_rays=8192, lr=1e-2, exp_step_factor=0.0, bg=(1.0, 1.0, 1.0), lambda_opacity=1e-3,
                  T_threshold=1e-4, betas=(0.9, 0.999), eps=1e-15, max_total_samples=None, update_interval=16,
@@ -144,21 +147,22 @@ class Trainer:
             f32 = dict(device=dev, dtype=torch.float32)
             i32 = dict(device=dev, dtype=torch.int32)
             N = self.n_rays
-            self.rays_o = torch.zeros(N, 3, **f32)
-            self.rays_d = torch.zeros(N, 3, **f32)
-            self.rgb_gt = torch.zeros(N, 3, **f32)
-            self.noise = torch.zeros(N, **f32)
+            # Two sets of everything the batch assembly + march WRITE and the network step READS (rays, jitter, per-ray
+            # counts, compacted samples, counters): the next step's batch is marched into the other set while this
+            # step's network forward / backward / optimiser run (capture(): deep pipeline).
+            self._sets = []
+            for _ in range(2):
+                self._sets.append(dict(
+                    rays_o=torch.zeros(N, 3, **f32), rays_d=torch.zeros(N, 3, **f32), rgb_gt=torch.zeros(N, 3, **f32),
+                    noise=torch.zeros(N, **f32), n_samples=torch.zeros(N, **i32), offsets=torch.zeros(N, **i32),
+                    counters=torch.zeros(8, **i32), ray_idx=torch.empty(cap, **i32), ts=torch.empty(cap, **f32),
+                    deltas=torch.empty(cap, **f32)))
+            self._cur = 0
             self.stage_t = torch.empty(N * MAX_SAMPLES, **f32)
             self.stage_dt = torch.empty(N * MAX_SAMPLES, **f32)
-            self.n_samples = torch.zeros(N, **i32)
-            self.offsets = torch.zeros(N, **i32)
-            self.counters = torch.zeros(8, **i32)
             self.rgb = torch.zeros(N, 3, **f32)
             self.opacity = torch.zeros(N, **f32)
             self.depth = torch.zeros(N, **f32)
-            self.ray_idx = torch.empty(cap, **i32)
-            self.ts = torch.empty(cap, **f32)
-            self.deltas = torch.empty(cap, **f32)
             self.sigmas = torch.empty(cap, **f32)
             self.rgbs = torch.empty(cap, 3, **f32)
             self.ws = torch.empty(cap, **f32) if materialize_ws else None
@@ -181,20 +185,23 @@ class Trainer:
                 self.dL_dws = torch.zeros(cap, **f32)
             scan_bytes = L.ngp_train_scan_temp_bytes(N)
             self.scan_temp = torch.empty(scan_bytes, device=dev, dtype=torch.uint8)
-            b = _lib.NgpTrainBuffers()
-            for name in ("rays_o", "rays_d", "noise", "stage_t", "stage_dt", "n_samples", "offsets", "counters", "rgb",
-                         "opacity", "depth", "ray_idx", "ts", "deltas", "sigmas", "rgbs", "dsigmas", "drgbs", "feat_save",
-                         "scalars", "scan_temp"):
-                setattr(b, name, getattr(self, name).data_ptr())
-            b.ws = self.ws.data_ptr() if self.ws is not None else None
-            b.live_idx = self.live_idx.data_ptr() if self.live_idx is not None else None
-            b.density_bitfield = model.density_bitfield.data_ptr()
-            b.scan_temp_bytes = scan_bytes
             bwd_bytes = L.ngp_net_backward_workspace(cap)
             self.bwd_ws = torch.empty(bwd_bytes, device=dev, dtype=torch.uint8)
-            b.bwd_workspace = self.bwd_ws.data_ptr()
-            b.bwd_workspace_bytes = bwd_bytes
-            self.buf = b
+            for st_ in self._sets:
+                b = _lib.NgpTrainBuffers()
+                for name in _SET_FIELDS:
+                    if name != "rgb_gt":
+                        setattr(b, name, st_[name].data_ptr())
+                for name in ("stage_t", "stage_dt", "rgb", "opacity", "depth", "sigmas", "rgbs", "dsigmas", "drgbs",
+                             "feat_save", "scalars", "scan_temp"):
+                    setattr(b, name, getattr(self, name).data_ptr())
+                b.ws = self.ws.data_ptr() if self.ws is not None else None
+                b.live_idx = self.live_idx.data_ptr() if self.live_idx is not None else None
+                b.density_bitfield = model.density_bitfield.data_ptr()
+                b.scan_temp_bytes = scan_bytes
+                b.bwd_workspace = self.bwd_ws.data_ptr()
+                b.bwd_workspace_bytes = bwd_bytes
+                st_["buf"] = b
 
             # ---- occupancy grid ----------------------------------------------------------------------------
             G3 = model.grid_size ** 3
@@ -210,6 +217,15 @@ class Trainer:
         self.bank = None
 
     # ------------------------------------------------------------------------------------------------------
+    def __getattr__(self, name):
+        # rays_o, rays_d, rgb_gt, noise, n_samples, offsets, counters, ray_idx, ts, deltas, buf: those of the set the
+        # current / last completed step works on
+        if name in _SET_FIELDS or name == "buf":
+            sets = self.__dict__.get("_sets")
+            if sets:
+                return sets[self.__dict__.get("_cur", 0)][name]
+        raise AttributeError(name)
+
     def _st(self):
         return torch.cuda.current_stream(self.dev).cuda_stream
 
@@ -232,27 +248,26 @@ class Trainer:
     def attach_bank(self, bank):
         """bank: synth.RayBank (directions, poses, uint8 images on the device)"""
         self.bank = bank
-        self.img_idx = torch.zeros(self.n_rays, device=self.dev, dtype=torch.int64)
-        self.pix_idx = torch.zeros(self.n_rays, device=self.dev, dtype=torch.int64)
 
     def sample_batch(self):
-        """random (image, pixel) pairs with replacement (reference datasets/base.py:22-30) + ray assembly"""
+        """random (image, pixel) pairs with replacement (reference datasets/base.py:22-30) + ray assembly + the march's
+        start jitter, one kernel with a device-side counter-based generator (one stream per buffer set)"""
         bk = self.bank
-        self.img_idx.random_(0, bk.poses.shape[0], generator=self.gen)
-        self.pix_idx.random_(0, bk.directions.shape[0], generator=self.gen)
-        rc = _lib.lib().ngp_gen_rays(self.img_idx.data_ptr(), self.pix_idx.data_ptr(), bk.poses.data_ptr(),
-                                     bk.directions.data_ptr(), bk.rgb.data_ptr(), bk.directions.shape[0], self.n_rays,
-                                     self.rays_o.data_ptr(), self.rays_d.data_ptr(), self.rgb_gt.data_ptr(), self._st())
-        _lib.check(rc, "gen_rays")
+        rc = _lib.lib().ngp_sample_rays(bk.poses.data_ptr(), bk.directions.data_ptr(), bk.rgb.data_ptr(), bk.poses.shape[0],
+                                        bk.directions.shape[0], self.n_rays, (self.seed * 2654435761 + 97 * self.rank) & 0xffffffff,
+                                        self._cur, self.counters[6:].data_ptr(), self.rays_o.data_ptr(), self.rays_d.data_ptr(),
+                                        self.rgb_gt.data_ptr(), self.noise.data_ptr(), self._st())
+        _lib.check(rc, "sample_rays")
 
     def set_batch(self, rays_o, rays_d, rgb_gt):
         self.rays_o.copy_(rays_o, non_blocking=True)
         self.rays_d.copy_(rays_d, non_blocking=True)
         self.rgb_gt.copy_(rgb_gt, non_blocking=True)
 
-    def march(self):
+    def march(self, jitter=True):
         """first half of the forward: start jitter + AABB + march + scan + compaction (independent of the weights)"""
-        self.noise.uniform_(0, 1, generator=self.gen)
+        if jitter:
+            self.noise.uniform_(0, 1, generator=self.gen)
         _lib.check(_lib.lib().ngp_render_train_march(C.byref(self.cfg), C.byref(self.buf), self._st()), "render_train_march")
 
     def network(self):
@@ -326,8 +341,8 @@ class Trainer:
     # ---- one optimiser step ----------------------------------------------------------------------------------
     def _prepare(self, sample):
         if sample:
-            self.sample_batch()
-        self.march()
+            self.sample_batch()  # draws the jitter too
+        self.march(jitter=not sample)
 
     def _compute(self):
         self.network()
@@ -343,12 +358,14 @@ class Trainer:
         self._update()
 
     def capture(self, sample=True):
-        """Record the step into CUDA graphs. Three graphs instead of one so that the weight-independent front
-        of the NEXT step (batch assembly + march) can replay on a side stream while the optimiser of THIS step
-        (Adam / all-reduce / the fused NVLink kernel) runs on the main stream:
-            g_prepare = [device RNG, ngp_gen_rays, march, scan, compaction]
-            g_compute = [network fwd, compositing, NeRFLoss, compositing bwd, loss scale, MLP bwd, scatter]
-            g_update  = [Adam]   (NCCL all-reduce / the p2p kernel and its barriers are launched eagerly)"""
+        """Record the step into CUDA graphs, one [prepare, compute] pair per buffer set plus the optimiser:
+            g_prepare[i] = [device RNG, ngp_gen_rays, march, scan, compaction]          -> writes set i
+            g_compute[i] = [network fwd, compositing, NeRFLoss, compositing bwd, loss scale, MLP bwd, scatter]  reads set i
+            g_update     = [Adam]   (NCCL all-reduce / the p2p kernel and its barriers are launched eagerly)
+        The front of a step (batch assembly + march) depends on the rays, the jitter and the occupancy bitfield but
+        NOT on the weights, so train_step() replays the NEXT step's g_prepare into the other buffer set on a side
+        stream while this step's g_compute and g_update run on the main stream (except across an occupancy refresh,
+        whose new bitfield the next march must see -- the reference's ordering, train.py:160-163)."""
         dev = self.dev
         s = torch.cuda.Stream(dev)
         s.wait_stream(torch.cuda.current_stream(dev))
@@ -364,12 +381,19 @@ class Trainer:
                 self.hG.barrier(channel=0)
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
-        self.g_prepare, self.g_compute, self.g_update = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), None
-        self.g_prepare.register_generator_state(self.gen)
-        with torch.cuda.graph(self.g_prepare):
-            self._prepare(sample)
-        with torch.cuda.graph(self.g_compute):
-            self._compute()
+        self.g_prepare, self.g_compute, self.g_update = [], [], None
+        keep = self._cur
+        for i in range(2):
+            self._cur = i
+            gp, gc = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            gp.register_generator_state(self.gen)
+            with torch.cuda.graph(gp):
+                self._prepare(sample)
+            with torch.cuda.graph(gc):
+                self._compute()
+            self.g_prepare.append(gp)
+            self.g_compute.append(gc)
+        self._cur = keep
         if self.ddp != "p2p":
             self.g_update = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.g_update):
@@ -377,6 +401,7 @@ class Trainer:
         self.graph = True
         self._graph_samples = sample
         self._side = torch.cuda.Stream(dev)
+        self._ev_compute = torch.cuda.Event()
         self._premarched = False
 
     def train_step(self, sample=True):
@@ -390,19 +415,28 @@ class Trainer:
             self.host_step += 1
             return
         main = torch.cuda.current_stream(self.dev)
-        if not self._premarched:
-            self.g_prepare.replay()
-        elif refresh:
-            # the batch was assembled and marched ahead of time against the previous bitfield: march the SAME rays
-            # and jitter again so that the step sees the refreshed grid, exactly like the reference's ordering
-            _lib.check(_lib.lib().ngp_render_train_march(C.byref(self.cfg), C.byref(self.buf), self._st()), "render_train_march")
-        self.g_compute.replay()
-        # overlap: the next step's batch + march (side stream) with this step's optimiser (main stream)
+        if self._premarched:
+            self._cur = 1 - self._cur  # the set the previous step marched ahead
+            if refresh:
+                # (not reached with the cadence below) marched against the previous bitfield: march the SAME rays and
+                # jitter again so that the step sees the refreshed grid, exactly like the reference's ordering
+                _lib.check(_lib.lib().ngp_render_train_march(C.byref(self.cfg), C.byref(self.buf), self._st()),
+                           "render_train_march")
+        else:
+            self.g_prepare[self._cur].replay()
+        # deep pipeline: the next step's batch + march into the OTHER set (side stream) under this whole step
         ahead = sample and ((self.host_step + 1) % self.update_interval != 0)
         if ahead:
-            self._side.wait_stream(main)
+            # the other set's last reader is the previous step's g_compute: once that is done (and this step's march, if it
+            # ran on the main stream, is enqueued) the next march may start -- it does not wait for the optimiser
+            if self._premarched:
+                self._side.wait_event(self._ev_compute)
+            else:
+                self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
-                self.g_prepare.replay()
+                self.g_prepare[1 - self._cur].replay()
+        self.g_compute[self._cur].replay()
+        self._ev_compute.record(main)
         self.allreduce()
         if self.g_update is not None:
             self.g_update.replay()

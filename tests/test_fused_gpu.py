@@ -126,6 +126,51 @@ def test_gen_rays_matches_reference_convention():
     assert torch.allclose(c, imgs[img, pix].float() / 255)
 
 
+def test_sample_rays_draws_uniform_pairs_and_builds_the_same_rays():
+    """ngp_sample_rays = device-side draw of (image, pixel) with replacement + ngp_gen_rays + jitter in one kernel."""
+    from ngp_pl_b200 import synth, _lib
+    scene = synth.lego_scene(0)
+    K = synth.intrinsics(W=40, H=30, fx=300.0)
+    bank = synth.RayBank(scene, n_images=7, K=K, device="cuda")
+    n_img, n_pix = bank.poses.shape[0], bank.directions.shape[0]
+    n = 20000
+    L = _lib.lib()
+
+    def draw(seed, stream, ctr):
+        o = torch.empty(n, 3, device="cuda"); d = torch.empty(n, 3, device="cuda"); c = torch.empty(n, 3, device="cuda")
+        z = torch.empty(n, device="cuda")
+        _lib.check(L.ngp_sample_rays(bank.poses.data_ptr(), bank.directions.data_ptr(), bank.rgb.data_ptr(), n_img, n_pix, n,
+                                     seed, stream, ctr.data_ptr(), o.data_ptr(), d.data_ptr(), c.data_ptr(), z.data_ptr(),
+                                     torch.cuda.current_stream().cuda_stream), "sample_rays")
+        return o, d, c, z
+    ctr = torch.zeros(2, dtype=torch.int32, device="cuda")
+    o, d, c, z = draw(5, 0, ctr)
+    assert ctr.tolist() == [1, 0]  # the kernel advanced its own draw counter
+    # every ray is exactly what ngp_gen_rays builds for SOME (image, pixel): recover the pair and compare
+    origins = bank.poses[:, :, 3]
+    im = (o[:, None, :] - origins[None]).abs().sum(-1).argmin(1)
+    assert torch.equal(o, origins[im])
+    all_d = torch.einsum("pc,ikc->ipk", bank.directions, bank.poses[:, :, :3])  # (n_img, n_pix, 3)
+    px = (all_d[im] - d[:, None, :]).abs().sum(-1).argmin(1)
+    o2 = torch.empty_like(o); d2 = torch.empty_like(d); c2 = torch.empty_like(c)
+    _lib.check(L.ngp_gen_rays(im.data_ptr(), px.data_ptr(), bank.poses.data_ptr(), bank.directions.data_ptr(),
+                              bank.rgb.data_ptr(), n_pix, n, o2.data_ptr(), d2.data_ptr(), c2.data_ptr(),
+                              torch.cuda.current_stream().cuda_stream), "gen_rays")
+    assert torch.equal(d, d2) and torch.equal(c, c2)
+    # uniform with replacement over images and pixels, jitter uniform in [0,1)
+    cnt = torch.bincount(im, minlength=n_img).float()
+    assert (cnt - n / n_img).abs().max() < 6 * (n / n_img) ** 0.5
+    assert torch.bincount(px, minlength=n_pix).max() <= 60 and px.unique().numel() > 0.99 * n_pix
+    assert 0 <= float(z.min()) and float(z.max()) < 1 and abs(float(z.mean()) - 0.5) < 0.01
+    # next draw differs; another stream differs; same (seed, stream, draw) reproduces
+    o3, d3, _, z3 = draw(5, 0, ctr)
+    assert not torch.equal(d3, d) and not torch.equal(z3, z)
+    o4, d4, _, _ = draw(5, 1, torch.zeros(2, dtype=torch.int32, device="cuda"))
+    assert not torch.equal(d4, d)
+    o5, d5, c5, z5 = draw(5, 0, torch.zeros(2, dtype=torch.int32, device="cuda"))
+    assert torch.equal(d5, d) and torch.equal(z5, z) and torch.equal(c5, c)
+
+
 def test_update_density_grid_semantics():
     from ngp_pl_b200 import synth, vren
     from ngp_pl_b200.trainer import Trainer
