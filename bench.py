@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--fps-views", type=int, default=5)
     ap.add_argument("--no-fps", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ddp", default="p2p", choices=["p2p", "nccl"],
+    ap.add_argument("--ddp", default="p2p", choices=["p2p", "nccl", "zero"],
                     help="N>1 gradient exchange: fused NVLink reduce-scatter+Adam+all-gather kernel, or NCCL all-reduce")
     return ap.parse_args()
 

@@ -86,3 +86,18 @@ def test_shard_range_partitions_exactly():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_zero_shards_partition_the_parameters():
+    """"zero" mode (reduce_scatter + sharded Adam + all_gather): equal 16-byte aligned shards that cover every parameter once"""
+    from ngp_pl_b200.trainer import zero_shard
+    for n in (12206080 + 3072 + 7168, 1001, 4, 7):
+        for world in (1, 2, 3, 4, 8):
+            covered = 0
+            for r in range(world):
+                lo, hi, n_pad = zero_shard(n, world, r)
+                assert n_pad % (4 * world) == 0 and n <= n_pad < n + 4 * world
+                assert (lo % 4 == 0 or hi == lo) and 0 <= lo <= hi <= n and hi - lo <= n_pad // world
+                assert lo == min(r * (n_pad // world), n)
+                covered += hi - lo
+            assert covered == n
