@@ -46,8 +46,10 @@ def parse():
     ap.add_argument("--fps-views", type=int, default=5)
     ap.add_argument("--no-fps", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ddp", default="p2p", choices=["p2p", "nccl", "zero"],
-                    help="N>1 gradient exchange: fused NVLink reduce-scatter+Adam+all-gather kernel, or NCCL all-reduce")
+    ap.add_argument("--ddp", default="auto", choices=["auto", "p2p", "nccl", "zero"],
+                    help="N>1 gradient exchange. p2p: fused NVLink reduce-scatter+Adam+all-gather kernel; zero: the same "
+                         "algorithm with NCCL reduce_scatter/all_gather; nccl: all-reduce + full Adam (the reference's DDP). "
+                         "auto = zero for 2 GPUs, p2p beyond (measured best, profiles/r01_bench_n*.log)")
     return ap.parse_args()
 
 
@@ -199,15 +201,15 @@ def run_b200(args):
     scene = synth.lego_scene(0)
     bank = synth.RayBank(scene, n_images=N_TRAIN_IMAGES, device=dev, seed=rank)  # every rank: own images order/sampling
     model = NGP(scene.scale).to(dev)
-    ddp_mode = args.ddp
+    ddp_mode = args.ddp if args.ddp != "auto" else ("zero" if world <= 2 else "p2p")
     try:
         tr = Trainer(model, n_rays=N_RAYS, lr=1e-2, process_group=pg, world_size=world, rank=rank, seed=rank, ddp=ddp_mode)
     except Exception as e:  # symmetric memory unavailable: fall back to NCCL and say so in the line
-        if world == 1 or ddp_mode == "nccl":
+        if world == 1 or ddp_mode != "p2p":
             raise
-        ddp_mode = "nccl (p2p unavailable: %s)" % type(e).__name__
+        ddp_mode = "zero (p2p unavailable: %s)" % type(e).__name__
         model = NGP(scene.scale).to(dev)
-        tr = Trainer(model, n_rays=N_RAYS, lr=1e-2, process_group=pg, world_size=world, rank=rank, seed=rank, ddp="nccl")
+        tr = Trainer(model, n_rays=N_RAYS, lr=1e-2, process_group=pg, world_size=world, rank=rank, seed=rank, ddp="zero")
     tr.attach_bank(bank)
     pretrain = args.pretrain if args.pretrain is not None else 1000
     K, W = args.steps, max(args.warmup, 3)
@@ -246,12 +248,15 @@ def run_b200(args):
     step_nosample = lambda: tr.train_step(sample=False)
 
     def e2e_step(i):
-        o, d, c = host[i % n_host]
-        tr.set_batch(o, d, c)
+        # step i consumes the batch staged before; the NEXT batch's host->device copy and march are enqueued (side stream)
+        # before this step's result is waited for, as any prefetching loader does -- every step still pays its own H2D
+        # copy and its own loss read-back inside the timed region
         step_nosample()
+        tr.stage_batch(*host[(i + 1) % n_host])
         out_host.copy_(tr.scalars, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(out_host[2])
+    tr.stage_batch(*host[0])
     for i in range(W):
         e2e_step(i)
     barrier(world)
@@ -337,7 +342,9 @@ def run_b200(args):
     if rank != 0:
         return
     per_update = 9  # kernels of ngp_update_density_grid for one cascade
-    launches = K * 13 + (K // tr.update_interval + 1) * per_update  # gen_rays, march, compact, fwd, 2 composite, loss, scale, bwd, scatter, adam, step_inc + 1 re-march on refresh steps
+    # per step: sample_rays, march, scan, compact | fwd, composite fw, (zero 2 scalars), loss, composite bw, loss scale,
+    # MLP bwd, scatter | adam, step_inc
+    launches = K * 14 + (K // tr.update_interval + 1) * per_update
     line = {
         "metric": "train_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
@@ -346,7 +353,9 @@ def run_b200(args):
         "config": {"workload": "BASELINE config 2: Lego 800x800, 8192 rays/step/GPU, L=16 T=2^19 F=2, Adam lr 1e-2, "
                                "occupancy refresh every 16 steps", "rays_per_step_per_gpu": N_RAYS, "global_rays_per_step": world * N_RAYS,
                    "parallelism": "dp%d" % world + ("" if world == 1 else " [%s]" % (
-                       "fused NVLink reduce-scatter+Adam+all-gather kernel" if ddp_mode == "p2p" else ddp_mode)),
+                       {"p2p": "fused NVLink reduce-scatter+Adam+all-gather kernel",
+                                                 "zero": "NCCL reduce_scatter + sharded Adam + all_gather(fp16 params)",
+                                                 "nccl": "NCCL all_reduce + full Adam"}.get(ddp_mode, ddp_mode))),
                    "pretrain_steps": pretrain,
                    "l2": "no explicit flush: each step streams params+grads+Adam moments (~230 MB) > 126 MB L2",
                    "samples_per_ray_marched": stats["rm_samples"] / N_RAYS, "samples_per_ray_composited": stats["vr_samples"] / N_RAYS,

@@ -236,6 +236,8 @@ class Trainer:
         self.graph = False
         self._graph_samples = None
         self._premarched = False
+        self._staged = None
+        self._inflight = False
         self.bank = None
 
     # ------------------------------------------------------------------------------------------------------
@@ -285,6 +287,24 @@ class Trainer:
         self.rays_o.copy_(rays_o, non_blocking=True)
         self.rays_d.copy_(rays_d, non_blocking=True)
         self.rgb_gt.copy_(rgb_gt, non_blocking=True)
+
+    def stage_batch(self, rays_o, rays_d, rgb_gt):
+        """Prefetch for host-fed training (train_step(sample=False)): copy the NEXT step's batch (pinned host or device
+        tensors) into the other buffer set and march it on the side stream, under whatever step is in flight. The next
+        train_step(sample=False) consumes it. Falls back to set_batch() when the step is not graph-captured."""
+        if not (self.graph and self._graph_samples is False):
+            return self.set_batch(rays_o, rays_d, rgb_gt)
+        nxt = 1 - self._cur if (self._inflight or self._premarched) else self._cur
+        st_ = self._sets[nxt]
+        ev = self._ev_set[nxt]
+        if ev is not None:
+            self._side.wait_event(ev)  # the set's last reader (the compute graph two steps back)
+        with torch.cuda.stream(self._side):
+            st_["rays_o"].copy_(rays_o, non_blocking=True)
+            st_["rays_d"].copy_(rays_d, non_blocking=True)
+            st_["rgb_gt"].copy_(rgb_gt, non_blocking=True)
+            self.g_prepare[nxt].replay()
+        self._staged = nxt
 
     def march(self, jitter=True):
         """first half of the forward: start jitter + AABB + march + scan + compaction (independent of the weights)"""
@@ -443,6 +463,9 @@ class Trainer:
         self._graph_samples = sample
         self._side = torch.cuda.Stream(dev)
         self._ev_compute = torch.cuda.Event()
+        self._ev_set = [None, None]
+        self._staged = None
+        self._inflight = False
         self._premarched = False
 
     def train_step(self, sample=True):
@@ -456,6 +479,26 @@ class Trainer:
             self.host_step += 1
             return
         main = torch.cuda.current_stream(self.dev)
+        if self._staged is not None:  # a host batch staged (copied + marched) by stage_batch()
+            self._cur = self._staged
+            self._staged = None
+            main.wait_stream(self._side)
+            if refresh:  # marched against the previous bitfield: same rays and jitter again, like the reference's ordering
+                _lib.check(_lib.lib().ngp_render_train_march(C.byref(self.cfg), C.byref(self.buf), self._st()),
+                           "render_train_march")
+            self.g_compute[self._cur].replay()
+            if self._ev_set[self._cur] is None:
+                self._ev_set[self._cur] = torch.cuda.Event()
+            self._ev_set[self._cur].record(main)
+            self.allreduce()
+            if self.g_update is not None:
+                self.g_update.replay()
+            else:
+                self.optimizer_step()
+            self._premarched = False
+            self._inflight = True
+            self.host_step += 1
+            return
         if self._premarched:
             self._cur = 1 - self._cur  # the set the previous step marched ahead
             if refresh:

@@ -110,7 +110,13 @@ def full(src, dst, traffic_json=None):
         out.append("")
     open(dst, "w").write("\n".join(out) + "\n")
     if traffic_json:
-        json.dump(traffic, open(traffic_json, "w"), indent=1)
+        merged = {}
+        try:
+            merged = json.load(open(traffic_json))  # one capture per kernel: keep the other kernels' entries
+        except Exception:
+            pass
+        merged.update(traffic)
+        json.dump(merged, open(traffic_json, "w"), indent=1)
     print("\n".join(out))
 
 
