@@ -43,6 +43,53 @@ __device__ __forceinline__ GridCell grid_cell(float x01, float y01, float z01, f
     return c;
 }
 
+// The 8 corner indices of a cell, k = dx + 2*dy + 4*dz. Same values as grid_corner_index() corner by corner, with the
+// per-axis terms shared: hashed = two xors per corner (LOP3), dense = one 3-input add + the boundary wrap.
+__device__ __forceinline__ void grid_corner_indices(const GridCell& c, uint32_t res, uint32_t entries, bool hashed,
+                                                    uint32_t (&idx)[8]) {
+    if (hashed) {
+        const uint32_t mask = entries - 1u;  // hashed levels always have 2^log2_T entries
+        const uint32_t x0 = c.gx, x1 = c.gx + 1u;
+        const uint32_t y0 = c.gy * 2654435761u, y1 = y0 + 2654435761u;
+        const uint32_t z0 = c.gz * 805459861u, z1 = z0 + 805459861u;
+        const uint32_t t00 = y0 ^ z0, t10 = y1 ^ z0, t01 = y0 ^ z1, t11 = y1 ^ z1;
+        idx[0] = (x0 ^ t00) & mask; idx[1] = (x1 ^ t00) & mask;
+        idx[2] = (x0 ^ t10) & mask; idx[3] = (x1 ^ t10) & mask;
+        idx[4] = (x0 ^ t01) & mask; idx[5] = (x1 ^ t01) & mask;
+        idx[6] = (x0 ^ t11) & mask; idx[7] = (x1 ^ t11) & mask;
+    } else {
+        const uint32_t r2 = res * res;
+        const uint32_t b00 = c.gx + c.gy * res + c.gz * r2;
+        const uint32_t b10 = b00 + res, b01 = b00 + r2, b11 = b10 + r2;
+        const uint32_t last = entries - 1u;
+        uint32_t v;
+        // one conditional subtract IS the modulo for inputs in the unit cube; the clamp keeps outside inputs memory-safe
+#define NGP_WRAP(dst, val) v = (val); v = v >= entries ? v - entries : v; dst = min(v, last)
+        NGP_WRAP(idx[0], b00); NGP_WRAP(idx[1], b00 + 1u);
+        NGP_WRAP(idx[2], b10); NGP_WRAP(idx[3], b10 + 1u);
+        NGP_WRAP(idx[4], b01); NGP_WRAP(idx[5], b01 + 1u);
+        NGP_WRAP(idx[6], b11); NGP_WRAP(idx[7], b11 + 1u);
+#undef NGP_WRAP
+    }
+}
+
+// the 8 trilinear weights, k = dx + 2*dy + 4*dz (same products as ((k&1)?wx:1-wx) * ((k&2)?wy:1-wy) * ((k&4)?wz:1-wz))
+__device__ __forceinline__ void grid_corner_weights(const GridCell& c, float (&w)[8]) {
+    const float ux = 1.0f - c.wx, uy = 1.0f - c.wy, uz = 1.0f - c.wz;
+    const float a00 = ux * uy, a10 = c.wx * uy, a01 = ux * c.wy, a11 = c.wx * c.wy;
+    w[0] = a00 * uz; w[1] = a10 * uz; w[2] = a01 * uz; w[3] = a11 * uz;
+    w[4] = a00 * c.wz; w[5] = a10 * c.wz; w[6] = a01 * c.wz; w[7] = a11 * c.wz;
+}
+
+// base + idx * BYTES as ONE IMAD.WIDE.U32 (the compiler otherwise folds the level offset back into a 64-bit add chain:
+// four instructions per corner)
+template <int BYTES>
+__device__ __forceinline__ const void* entry_ptr(const void* base, uint32_t idx) {
+    uint64_t a;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(idx), "n"(BYTES), "l"((uint64_t)base));
+    return (const void*)a;
+}
+
 // Trilinear lookup of one (sample, level): 8 independent 4-byte gathers, then 8 FMAs per feature.
 __device__ __forceinline__ float2 grid_lookup(const uint32_t* __restrict__ table /* half2 per entry */,
                                               const NgpGridMeta& m, int level, float x01, float y01, float z01) {
@@ -51,19 +98,19 @@ __device__ __forceinline__ float2 grid_lookup(const uint32_t* __restrict__ table
     const uint32_t entries = m.offset[level + 1] - off;
     const bool hashed = (m.hashed_mask >> level) & 1u;
     const GridCell c = grid_cell(x01, y01, z01, m.scale[level]);
-    uint32_t v[8];
+    uint32_t idx[8], v[8];
+    grid_corner_indices(c, res, entries, hashed, idx);
+    const uint32_t* lvl = table + off;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const uint32_t px = c.gx + (k & 1), py = c.gy + ((k >> 1) & 1), pz = c.gz + ((k >> 2) & 1);
-        v[k] = __ldg(table + off + grid_corner_index(px, py, pz, res, entries, hashed));
-    }
+    for (int k = 0; k < 8; ++k) v[k] = __ldg(reinterpret_cast<const uint32_t*>(entry_ptr<4>(lvl, idx[k])));
+    float w[8];
+    grid_corner_weights(c, w);
     float f0 = 0.f, f1 = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const float w = ((k & 1) ? c.wx : 1.0f - c.wx) * ((k & 2) ? c.wy : 1.0f - c.wy) * ((k & 4) ? c.wz : 1.0f - c.wz);
         const float2 t = unpack_half2(v[k]);
-        f0 = fmaf(w, t.x, f0);
-        f1 = fmaf(w, t.y, f1);
+        f0 = fmaf(w[k], t.x, f0);
+        f1 = fmaf(w[k], t.y, f1);
     }
     return make_float2(f0, f1);
 }
@@ -76,13 +123,14 @@ __device__ __forceinline__ void grid_scatter(float* __restrict__ grad /* float2 
     const uint32_t entries = m.offset[level + 1] - off;
     const bool hashed = (m.hashed_mask >> level) & 1u;
     const GridCell c = grid_cell(x01, y01, z01, m.scale[level]);
+    uint32_t idx[8];
+    grid_corner_indices(c, res, entries, hashed, idx);
+    float w[8];
+    grid_corner_weights(c, w);
+    const float* lvl = grad + 2 * (size_t)off;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const uint32_t px = c.gx + (k & 1), py = c.gy + ((k >> 1) & 1), pz = c.gz + ((k >> 2) & 1);
-        const uint32_t idx = off + grid_corner_index(px, py, pz, res, entries, hashed);
-        const float w = ((k & 1) ? c.wx : 1.0f - c.wx) * ((k & 2) ? c.wy : 1.0f - c.wy) * ((k & 4) ? c.wz : 1.0f - c.wz);
-        red_add_f32x2(grad + 2 * (size_t)idx, w * g0, w * g1);
-    }
+    for (int k = 0; k < 8; ++k)
+        red_add_f32x2(const_cast<float*>(reinterpret_cast<const float*>(entry_ptr<8>(lvl, idx[k]))), w[k] * g0, w[k] * g1);
 }
 
 // Degree-4 real spherical harmonics of a unit vector (16 coefficients), tiny-cuda-nn's ordering and

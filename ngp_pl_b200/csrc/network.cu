@@ -1002,11 +1002,14 @@ k_grid_scatter_merged(const NgpNet net, const NgpSamples smp, const uint32_t* __
                 gr.y *= inv_scale;
             }
             float acc[16];
+            {
+                float wk[8];
+                grid_corner_weights(c, wk);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float wk = ((k & 1) ? c.wx : 1.0f - c.wx) * ((k & 2) ? c.wy : 1.0f - c.wy) * ((k & 4) ? c.wz : 1.0f - c.wz);
-                acc[2 * k] = wk * gr.x;
-                acc[2 * k + 1] = wk * gr.y;
+                for (int k = 0; k < 8; ++k) {
+                    acc[2 * k] = wk[k] * gr.x;
+                    acc[2 * k + 1] = wk[k] * gr.y;
+                }
             }
             // runs of equal cells (an invalid lane never joins a run)
             const uint32_t px = __shfl_up_sync(0xffffffffu, c.gx, 1), py = __shfl_up_sync(0xffffffffu, c.gy, 1),
@@ -1034,12 +1037,13 @@ k_grid_scatter_merged(const NgpNet net, const NgpSamples smp, const uint32_t* __
                 }
             }
             if (valid && head) {
+                uint32_t idx[8];
+                grid_corner_indices(c, res, entries, hashed, idx);
+                const float* lvl = grad_table + 2 * (size_t)off;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint32_t qx = c.gx + (k & 1), qy = c.gy + ((k >> 1) & 1), qz = c.gz + ((k >> 2) & 1);
-                    const uint32_t idx = off + grid_corner_index(qx, qy, qz, res, entries, hashed);
-                    red_add_f32x2(grad_table + 2 * (size_t)idx, acc[2 * k], acc[2 * k + 1]);
-                }
+                for (int k = 0; k < 8; ++k)
+                    red_add_f32x2(const_cast<float*>(reinterpret_cast<const float*>(entry_ptr<8>(lvl, idx[k]))), acc[2 * k],
+                                  acc[2 * k + 1]);
             }
         }
     }
