@@ -342,9 +342,9 @@ def run_b200(args):
     if rank != 0:
         return
     per_update = 9  # kernels of ngp_update_density_grid for one cascade
-    # per step: sample_rays, march, scan, compact | fwd, composite fw, (zero 2 scalars), loss, composite bw, loss scale,
-    # MLP bwd, scatter | adam, step_inc
-    launches = K * 14 + (K // tr.update_interval + 1) * per_update
+    # per step: sample_rays, march, scan, compact | fwd, composite fw + loss + composite bw, loss scale, MLP bwd, scatter |
+    # adam, step_inc
+    launches = K * 11 + (K // tr.update_interval + 1) * per_update
     line = {
         "metric": "train_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",

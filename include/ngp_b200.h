@@ -238,7 +238,8 @@ typedef struct {
     int32_t* live_idx;            /* (S) optional: samples with a non-zero upstream gradient, built by the compositing
                                      backward; the network backward then visits only those */
     void* feat_save;              /* ceil32(S)*64 bytes */
-    float* scalars;               /* [0] amax scratch, [1] loss scale, [2] sum sq err, [3] sum opacity entropy */
+    float* scalars;               /* float[8]: [0] amax scratch, [1] loss scale, [2] sum sq err, [3] sum opacity entropy of the last
+                                     step, [4],[5] their accumulators inside ngp_render_train_step (zero otherwise) */
     void* scan_temp;
     size_t scan_temp_bytes;
     void* bwd_workspace;          /* ngp_net_backward_workspace(max_total_samples) bytes */
@@ -253,6 +254,13 @@ int ngp_render_train_fwd(const NgpNet* net, const NgpTrainCfg* cfg, const NgpTra
  * optimiser of the previous step) and _net (network + compositing). _fwd == _march then _net. */
 int ngp_render_train_march(const NgpTrainCfg* cfg, const NgpTrainBuffers* buf, void* stream);
 int ngp_render_train_net(const NgpNet* net, const NgpTrainCfg* cfg, const NgpTrainBuffers* buf, void* stream);
+
+/* Weight-dependent part of one training step with the plain NeRFLoss (losses.py:47-60, no distortion term) in one call:
+ * network forward -> ONE kernel for {compositing forward, loss + its per-ray gradients, compositing backward} -> loss
+ * scale -> MLP backward -> table scatter. Equivalent to ngp_render_train_net + ngp_nerf_loss_grad + ngp_render_train_bwd
+ * (needs dsigmas, drgbs, feat_save; fills rgb/opacity/depth, scalars[2..3], counters[2..3]). */
+int ngp_render_train_step(const NgpNet* net, const NgpTrainCfg* cfg, const NgpTrainBuffers* b, const float* rgb_gt,
+                          float* grad_enc, float* grad_rgb, void* stream);
 
 /* backward from per-ray gradients (dL_ddepth / dL_dws may be NULL = 0); accumulates (+=) into the
  * fp32 gradient vectors laid out like the parameter vectors. */

@@ -19,6 +19,7 @@ struct MarchConst {
     float esf;           // exp_step_factor
     float dt_lo, dt_hi;  // clamp bounds of the step (reference raymarching.cu:11-13)
     float gs_f, gs_inv, gs_m1;
+    float mb0, mb0_inv;  // mip 0: min(2^-1, scale) and its reciprocal (all a single-cascade grid ever uses)
 };
 
 // dt_scale is what the reference hands to calc_dt as `scale`: NGP.scale for the train kernel
@@ -38,6 +39,8 @@ __device__ __forceinline__ MarchConst make_march_const(const uint8_t* bitfield, 
     c.gs_m1 = __fadd_rn(c.gs_f, -1.0f);
     c.dt_lo = __fdiv_rn(1.73205080757f, (float)max_samples);
     c.dt_hi = __fdiv_rn(__fmul_rn(dt_scale, 3.46410161514f), c.gs_f);
+    c.mb0 = fminf(0.5f, scale);
+    c.mb0_inv = __fdiv_rn(1.0f, c.mb0);
     return c;
 }
 
@@ -186,8 +189,8 @@ __device__ __forceinline__ MarchProbe march_probe(const MarchRay& r, const March
     int mip = 0;
     float mip_bound, mip_bound_inv;
     if (ONE_CASCADE) {
-        mip_bound = fminf(0.5f, c.scale);
-        mip_bound_inv = __fdiv_rn(1.0f, mip_bound);
+        mip_bound = c.mb0;
+        mip_bound_inv = c.mb0_inv;
     } else {
         int e_pos, e_dt;
         frexpf(fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z))), &e_pos);
@@ -289,7 +292,37 @@ __device__ __forceinline__ int march_ray_warp(const MarchRay& ray, const MarchCo
             pending = (m == 0u);
         }
         unsigned sample_mask = 0u;
-        while (cur < 32) {
+        // The walk is the orbit of `cur` under  succ(j) = 32 (j past the box: stop) | j+1 (occupied: a sample) | nxt_j (empty).
+        // Pointer jumping gives the whole visited set in 5 rounds (one warp reduction + one shuffle each) instead of a
+        // dependent iteration per visit.
+        const int room0 = max_new - n;
+        if (room0 > 32) {
+            // more budget than points in the block: every visited occupied point is a sample
+            unsigned visited = cur < 32 ? (1u << cur) : 0u;
+            int jump = !valid ? 32 : (pr.occ ? lane + 1 : nxt);
+#pragma unroll
+            for (int r = 0; r < 5; ++r) {
+                const unsigned contrib = (((visited >> lane) & 1u) && jump < 32) ? (1u << jump) : 0u;
+                visited |= __reduce_or_sync(0xffffffffu, contrib);
+                const int jj = __shfl_sync(0xffffffffu, jump, jump & 31);
+                jump = jump < 32 ? jj : 32;
+            }
+            sample_mask = visited & occ_mask;
+            const unsigned exits = visited & ~valid_mask;  // at most one: succ(invalid) stops the orbit
+            if (exits) {  // t >= t2: the ray left the box
+                alive = false;
+                resume = __shfl_sync(0xffffffffu, p, __ffs(exits) - 1);
+            } else if (visited) {
+                // the last visited point: an empty one jumped past this block (carry its target over), an occupied one is
+                // lane 31 and the walk simply continues with the next block
+                const int last = 31 - __clz(visited);
+                if (!((occ_mask >> last) & 1u)) {
+                    pending = true;
+                    skip_to = __shfl_sync(0xffffffffu, pr.t_target, last);
+                }
+            }
+        } else
+        while (cur < 32) {  // the budget may run out inside this block (test-time rounds, max_samples): the literal walk
             if (!((valid_mask >> cur) & 1u)) {  // t >= t2: the ray left the box
                 alive = false;
                 resume = __shfl_sync(0xffffffffu, p, cur);

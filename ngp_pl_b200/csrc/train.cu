@@ -284,6 +284,15 @@ __global__ void k_train_grad_scale(float* __restrict__ scalars, int* __restrict_
     // whenever a compositing backward starts, whatever the caller's order of calls
     counters[5] = counters[4];
     counters[4] = 0;
+    // fused compositing + loss kernel: publish its sums ([4],[5] -> [2],[3]) and this step's sample counts, re-arm
+    if (scalars[4] != 0.f || scalars[5] != 0.f) {
+        scalars[2] = scalars[4];
+        scalars[3] = scalars[5];
+        scalars[4] = 0.f;
+        scalars[5] = 0.f;
+        counters[2] = counters[0];
+        counters[3] = counters[1];
+    }
     const float m = scalars[0];
     float s = 1.0f;
     if (m > 0.f && m < INFINITY) {
@@ -294,6 +303,101 @@ __global__ void k_train_grad_scale(float* __restrict__ scalars, int* __restrict_
     }
     scalars[1] = s;
     scalars[0] = 0.f;
+}
+
+// compositing forward + NeRFLoss + compositing backward of one ray in ONE pass by one warp (the loss gradient of a ray
+// depends on that ray's composited colour / opacity only): k_train_composite_fw + k_nerf_loss_grad + k_train_composite_bw
+// without the two extra launches and with the second sweep over the ray's samples hitting L1/L2.
+__global__ void k_train_composite_loss(const NgpTrainCfg cfg, const int* __restrict__ n_samples, const int* __restrict__ offsets,
+                                       const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                       const float* __restrict__ deltas, const float* __restrict__ ts,
+                                       const float* __restrict__ rgb_gt, float* __restrict__ rgb, float* __restrict__ opacity,
+                                       float* __restrict__ depth, float* __restrict__ dsigmas, float* __restrict__ drgbs,
+                                       float* __restrict__ scalars, int* __restrict__ live_idx, int* __restrict__ counters) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= cfg.n_rays) return;
+    const int64_t start = offsets[w];
+    int n = n_samples[w];
+    if (start + n > cfg.max_total_samples) n = (int)max((int64_t)0, cfg.max_total_samples - start);
+    const float* sg = sigmas + start;
+    const float* dl = deltas + start;
+    const float* tt = ts + start;
+    const float* cl = rgbs + 3 * start;
+    const CompositeOut o = composite_ray_warp(
+        n, cfg.T_threshold, lane,
+        [&](int i) { return __ldg(sg + i); }, [&](int i) { return __ldg(dl + i); }, [&](int i) { return __ldg(tt + i); },
+        [&](int i) { return make_float3(__ldg(cl + 3 * i), __ldg(cl + 3 * i + 1), __ldg(cl + 3 * i + 2)); },
+        [&](int, float) {});
+    const float rest = 1.0f - o.opacity;  // rgb += bg * (1 - opacity), reference rendering.py:160-161
+    const float3 out = make_float3(o.r + cfg.bg[0] * rest, o.g + cfg.bg[1] * rest, o.b + cfg.bg[2] * rest);
+    // NeRFLoss (reference losses.py:47-60, lambda_distortion = 0) and its per-ray gradients
+    const float inv_n = 1.0f / (float)cfg.n_rays;
+    const float ex = out.x - rgb_gt[3 * w], ey = out.y - rgb_gt[3 * w + 1], ez = out.z - rgb_gt[3 * w + 2];
+    const float3 dC = make_float3(2.0f * ex * inv_n * (1.0f / 3.0f), 2.0f * ey * inv_n * (1.0f / 3.0f), 2.0f * ez * inv_n * (1.0f / 3.0f));
+    const float op = o.opacity + 1e-10f;
+    const float lg = logf(op);
+    if (lane == 0) {
+        opacity[w] = o.opacity;
+        depth[w] = o.depth;
+        rgb[3 * w] = out.x; rgb[3 * w + 1] = out.y; rgb[3 * w + 2] = out.z;
+        if (o.total_samples) atomicAdd(&counters[1], o.total_samples);
+        atomicAdd(&scalars[4], ex * ex + ey * ey + ez * ez);
+        atomicAdd(&scalars[5], -op * lg);
+    }
+    if (n == 0) return;
+    // backward: the background term routes the colour gradient into the opacity gradient
+    const float dO = cfg.lambda_opacity * (-lg - 1.0f) * inv_n - (dC.x * cfg.bg[0] + dC.y * cfg.bg[1] + dC.z * cfg.bg[2]);
+    float* ds = dsigmas + start;
+    float* dc = drgbs + 3 * start;
+    float m = 0.f;
+    const int n_comp = composite_ray_warp_bwd(
+        n, cfg.T_threshold, lane, dO, 0.f, dC, o.opacity, o.depth, make_float3(o.r, o.g, o.b),
+        [&](int i) { return __ldg(sg + i); }, [&](int i) { return __ldg(dl + i); }, [&](int i) { return __ldg(tt + i); },
+        [&](int i) { return make_float3(__ldg(cl + 3 * i), __ldg(cl + 3 * i + 1), __ldg(cl + 3 * i + 2)); },
+        [&](int) { return 0.f; }, [&](int) { return 0.f; },
+        [&](int i, float v) {
+            ds[i] = v;
+            m = fmaxf(m, fabsf(v * fminf(__ldg(sg + i), 3.2690173e6f)));
+        },
+        [&](int i, float3 v) {
+            dc[3 * i] = v.x; dc[3 * i + 1] = v.y; dc[3 * i + 2] = v.z;
+            m = fmaxf(m, fmaxf(fabsf(v.x), fmaxf(fabsf(v.y), fabsf(v.z))));
+        });
+    m = warp_max(m);
+    if (lane == 0 && m > 0.f && m < INFINITY) atomicMax(reinterpret_cast<int*>(scalars), __float_as_int(m));
+    if (live_idx) {
+        int at = 0;
+        if (lane == 0) at = atomicAdd(&counters[4], n_comp);
+        at = __shfl_sync(0xffffffffu, at, 0);
+        for (int i = lane; i < n_comp; i += 32) live_idx[at + i] = (int)(start + i);
+    }
+}
+
+// One call for the weight-dependent part of a training step with the plain NeRFLoss (no distortion term):
+// network forward -> {compositing, loss, compositing backward} -> loss scale -> MLP backward -> table scatter.
+extern "C" int ngp_render_train_step(const NgpNet* net, const NgpTrainCfg* cfg, const NgpTrainBuffers* b, const float* rgb_gt,
+                                     float* grad_enc, float* grad_rgb, void* stream) {
+    int rc = check_train_args(net, cfg, b);
+    if (rc) return rc;
+    if (!rgb_gt || !b->dsigmas || !b->drgbs || !b->feat_save || !grad_enc || !grad_rgb) return NGP_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = cfg->n_rays;
+    NgpSamples smp = train_samples(cfg, b);
+    rc = ngp_net_forward(net, &smp, 1, b->sigmas, b->rgbs, nullptr, b->feat_save, stream);
+    if (rc) return rc;
+    k_train_composite_loss<<<ngp_div_up((int64_t)n * 32, 128), 128, 0, st>>>(
+        *cfg, b->n_samples, b->offsets, b->sigmas, b->rgbs, b->deltas, b->ts, rgb_gt, b->rgb, b->opacity, b->depth, b->dsigmas,
+        b->drgbs, b->scalars, b->live_idx, b->counters);
+    NGP_CHECK_LAUNCH();
+    k_train_grad_scale<<<1, 1, 0, st>>>(b->scalars, b->counters);
+    NGP_CHECK_LAUNCH();
+    if (b->live_idx) {
+        smp.live_idx = b->live_idx;
+        smp.n_live_dev = b->counters + 5;
+    }
+    return ngp_net_backward(net, &smp, b->dsigmas, b->drgbs, b->feat_save, b->scalars + 1, grad_enc, grad_rgb,
+                            b->bwd_workspace, b->bwd_workspace_bytes, stream);
 }
 
 extern "C" int ngp_render_train_bwd(const NgpNet* net, const NgpTrainCfg* cfg, const NgpTrainBuffers* b,
@@ -380,29 +484,46 @@ __global__ void k_adam(float* __restrict__ p, float* __restrict__ g, float* __re
     // fp32 params, moments and the consumed gradients stream through L2 (evict first); the fp16 working copy the
     // forward gathers from is kept (evict last); the zeroed gradients (next step's reduction target) stay normal
     const uint64_t stream_pol = l2_policy_evict_first(), keep_pol = l2_policy_evict_last();
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-        float4 pv = ld_f4_hint(reinterpret_cast<const float4*>(p) + i, stream_pol);
-        float4 gv = ld_f4_hint(reinterpret_cast<const float4*>(g) + i, stream_pol);
-        float4 mv = ld_f4_hint(reinterpret_cast<const float4*>(m) + i, stream_pol);
-        float4 vv = ld_f4_hint(reinterpret_cast<const float4*>(v) + i, stream_pol);
-        float* pp = &pv.x; float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
+    // two 64-byte groups per thread and trip: all eight 128-bit loads are issued before the first use, so the stream keeps
+    // ~15 MB in flight even when the next step's march shares the SMs' issue slots
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < n4; i0 += 2 * stride) {
+        const int64_t i1 = i0 + stride;
+        const bool two = i1 < n4;
+        float4 pv[2], gv[2], mv[2], vv[2];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float gr = gp[k] * grad_mul;
-            mp[k] = beta1 * mp[k] + (1.0f - beta1) * gr;
-            vp[k] = beta2 * vp[k] + (1.0f - beta2) * gr * gr;
-            const float denom = sqrtf(vp[k]) * inv_sqrt_bc2 + eps;
-            pp[k] -= step_size * (mp[k] / denom);
+        for (int u = 0; u < 2; ++u) {
+            const int64_t i = u ? i1 : i0;
+            if (u == 0 || two) {
+                pv[u] = ld_f4_hint(reinterpret_cast<const float4*>(p) + i, stream_pol);
+                gv[u] = ld_f4_hint(reinterpret_cast<const float4*>(g) + i, stream_pol);
+                mv[u] = ld_f4_hint(reinterpret_cast<const float4*>(m) + i, stream_pol);
+                vv[u] = ld_f4_hint(reinterpret_cast<const float4*>(v) + i, stream_pol);
+            }
         }
-        st_f4_hint(reinterpret_cast<float4*>(p) + i, pv, stream_pol);
-        st_f4_hint(reinterpret_cast<float4*>(m) + i, mv, stream_pol);
-        st_f4_hint(reinterpret_cast<float4*>(v) + i, vv, stream_pol);
-        reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ph) {
-            uint2 h;
-            h.x = pack_half2(pv.x, pv.y);
-            h.y = pack_half2(pv.z, pv.w);
-            st_u2_hint(reinterpret_cast<uint2*>(ph) + i, h, keep_pol);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !two) break;
+            const int64_t i = u ? i1 : i0;
+            float* pp = &pv[u].x; float* gp = &gv[u].x; float* mp = &mv[u].x; float* vp = &vv[u].x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float gr = gp[k] * grad_mul;
+                mp[k] = beta1 * mp[k] + (1.0f - beta1) * gr;
+                vp[k] = beta2 * vp[k] + (1.0f - beta2) * gr * gr;
+                const float denom = sqrtf(vp[k]) * inv_sqrt_bc2 + eps;
+                pp[k] -= step_size * (mp[k] / denom);
+            }
+            st_f4_hint(reinterpret_cast<float4*>(p) + i, pv[u], stream_pol);
+            st_f4_hint(reinterpret_cast<float4*>(m) + i, mv[u], stream_pol);
+            st_f4_hint(reinterpret_cast<float4*>(v) + i, vv[u], stream_pol);
+            reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ph) {
+                uint2 h;
+                h.x = pack_half2(pv[u].x, pv[u].y);
+                h.y = pack_half2(pv[u].z, pv[u].w);
+                st_u2_hint(reinterpret_cast<uint2*>(ph) + i, h, keep_pol);
+            }
         }
     }
     // tail

@@ -66,7 +66,7 @@ class Trainer:
     def __init__(self, model: NGP, n_rays=8192, lr=1e-2, exp_step_factor=0.0, bg=(1.0, 1.0, 1.0), lambda_opacity=1e-3,
                  T_threshold=1e-4, betas=(0.9, 0.999), eps=1e-15, max_total_samples=None, update_interval=16,
                  warmup_steps=256, process_group=None, world_size=1, rank=0, seed=0, materialize_ws=False, ddp="nccl",
-                 lambda_distortion=0.0, skip_dead_samples=True):
+                 lambda_distortion=0.0, skip_dead_samples=True, fused_loss=True):
         self.model = model
         dev = model.density_bitfield.device
         if dev.type != "cuda":
@@ -83,6 +83,8 @@ class Trainer:
             materialize_ws = True
         self.host_step = 0
         self.seed = seed
+        # the distortion loss needs the per-sample weights between the compositing forward and backward: separate kernels
+        self.fused_loss = bool(fused_loss) and not (lambda_distortion > 0) and not materialize_ws
         # "nccl": all_reduce of the flat gradient + full Adam on every rank (what the reference's DDP does);
         # "zero": NCCL reduce_scatter of the gradient + Adam on this rank's 1/N shard + all_gather of the fp16 working
         #         copy: 3/4 of all_reduce's traffic ((N-1)/N * (4+2) instead of 2*(N-1)/N * 4 bytes per parameter) and 1/N of
@@ -406,6 +408,12 @@ class Trainer:
         self.march(jitter=not sample)
 
     def _compute(self):
+        if self.fused_loss:
+            # plain NeRFLoss: compositing forward + loss + compositing backward are one kernel (ngp_render_train_step)
+            _lib.check(_lib.lib().ngp_render_train_step(C.byref(self.net), C.byref(self.cfg), C.byref(self.buf),
+                                                        self.rgb_gt.data_ptr(), self.G.data_ptr(),
+                                                        self.G[self.n_enc:].data_ptr(), self._st()), "render_train_step")
+            return
         self.network()
         self.loss_backward()
 

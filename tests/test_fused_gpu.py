@@ -440,3 +440,35 @@ def test_stage_batch_prefetch_matches_set_batch():
     assert logs[0][0][0] == logs[1][0][0] > 0 and abs(logs[0][0][1] - logs[1][0][1]) < 1e-6  # first step: identical inputs
     for (n0, l0), (n1, l1) in zip(*logs):
         assert abs(n0 - n1) <= 0.02 * n0 and abs(l0 - l1) <= 0.02 * l0  # later: atomics-order noise through Adam only
+
+
+def test_fused_composite_loss_kernel_matches_separate_kernels():
+    """ngp_render_train_step (compositing fw + NeRFLoss + compositing bw in one kernel) against
+    ngp_render_train_net + ngp_nerf_loss_grad + ngp_render_train_bwd on the same batch and jitter."""
+    from ngp_pl_b200 import synth
+    from ngp_pl_b200.trainer import Trainer
+    scene = synth.lego_scene(0)
+    n = 4096
+    o_np, d_np = cases.rays_from_scene(scene, n, 47, extra_edge_cases=True)
+    o, d = torch.as_tensor(o_np).cuda(), torch.as_tensor(d_np).cuda()
+    gt = torch.rand(n, 3, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+    noise = torch.rand(n, device="cuda", generator=torch.Generator("cuda").manual_seed(2))
+    out = {}
+    for fused in (True, False):
+        model = make_model(scene, amp=1.0)
+        tr = Trainer(model, n_rays=n, fused_loss=fused)
+        assert tr.fused_loss == fused
+        tr.set_batch(o, d, gt)
+        tr.noise.copy_(noise)
+        tr.march(jitter=False)
+        tr._compute()
+        torch.cuda.synchronize()
+        out[fused] = (tr.G.clone(), tr.stats(), tr.rgb.clone(), tr.opacity.clone(), tr.depth.clone(), float(tr.scalars[1]))
+    a, b = out[True], out[False]
+    for k in ("rm_samples", "vr_samples", "bw_samples"):
+        assert a[1][k] == b[1][k] > 0, k
+    assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3]) and torch.equal(a[4], b[4])  # same forward code
+    assert abs(a[1]["loss"] - b[1]["loss"]) < 1e-6 * max(1.0, abs(b[1]["loss"]))
+    assert a[5] == b[5]  # same power-of-two loss scale
+    s = b[0].abs().max().item()
+    assert s > 0 and (a[0] - b[0]).abs().max().item() < 2e-4 * s
