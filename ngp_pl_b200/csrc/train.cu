@@ -536,6 +536,89 @@ __global__ void k_adam(float* __restrict__ p, float* __restrict__ g, float* __re
         if (ph) ph[i] = __float2half_rn(p[i]);
     }
 }
+// (Experiment, NGP_ADAM_VARIANT=1; slower than k_adam inside the pipelined step, see ngp_adam_step.)
+// The same update with the stream staged through SHARED memory: every thread keeps ADAM_STAGES-1 tiles of (param, grad, m,
+// v) in flight as 16-byte cp.async copies into its own shared-memory slots (no barrier: a thread consumes only what it
+// copied itself). The ~12 MB that must be in flight to saturate HBM then live in shared memory, not in registers, so the
+// kernel needs one 256-thread CTA per SM and ~10 K registers of it -- the next step's march, which the trainer runs under
+// this kernel on another stream and which needs registers but no shared memory, keeps almost its full occupancy.
+#define ADAM_THREADS 256
+#define ADAM_STAGES 6
+__device__ __forceinline__ void cp_async16_hint(void* smem_dst, const void* gmem_src, uint64_t policy) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "l"(policy) : "memory");
+}
+__global__ void __launch_bounds__(ADAM_THREADS, 1)
+k_adam_staged(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+              __half* __restrict__ ph, int64_t n, const float* __restrict__ lr_dev, const int* __restrict__ step_dev, float beta1,
+              float beta2, float eps, float grad_mul) {
+    extern __shared__ __align__(16) float4 adam_buf[];  // [stage][array 0..3][thread]
+    const int t = *step_dev + 1;
+    const float lr = *lr_dev;
+    const float bc1 = 1.0f - powf(beta1, (float)t);
+    const float bc2 = 1.0f - powf(beta2, (float)t);
+    const float step_size = lr / bc1;
+    const float inv_sqrt_bc2 = rsqrtf(bc2);
+    const int64_t n4 = n >> 2;
+    const int64_t n_tiles = (n4 + ADAM_THREADS - 1) / ADAM_THREADS;
+    const uint64_t stream_pol = l2_policy_evict_first(), keep_pol = l2_policy_evict_last();
+    const int tid = threadIdx.x;
+    auto slot = [&](int stage, int arr) { return adam_buf + ((size_t)stage * 4 + arr) * ADAM_THREADS + tid; };
+    auto issue = [&](int64_t tile, int stage) {
+        const int64_t i = tile * ADAM_THREADS + tid;
+        if (tile < n_tiles && i < n4) {
+            cp_async16_hint(slot(stage, 0), reinterpret_cast<const float4*>(p) + i, stream_pol);
+            cp_async16_hint(slot(stage, 1), reinterpret_cast<const float4*>(g) + i, stream_pol);
+            cp_async16_hint(slot(stage, 2), reinterpret_cast<const float4*>(m) + i, stream_pol);
+            cp_async16_hint(slot(stage, 3), reinterpret_cast<const float4*>(v) + i, stream_pol);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");  // one group per tile, empty or not
+    };
+#pragma unroll
+    for (int s = 0; s < ADAM_STAGES - 1; ++s) issue((int64_t)blockIdx.x + (int64_t)s * gridDim.x, s);
+    int stage = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        issue(tile + (int64_t)(ADAM_STAGES - 1) * gridDim.x, (stage + ADAM_STAGES - 1) % ADAM_STAGES);
+        asm volatile("cp.async.wait_group %0;" ::"n"(ADAM_STAGES - 1) : "memory");  // this tile's group has landed
+        const int64_t i = tile * ADAM_THREADS + tid;
+        if (i < n4) {
+            float4 pv = *slot(stage, 0), gv = *slot(stage, 1), mv = *slot(stage, 2), vv = *slot(stage, 3);
+            float* pp = &pv.x; float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float gr = gp[k] * grad_mul;
+                mp[k] = beta1 * mp[k] + (1.0f - beta1) * gr;
+                vp[k] = beta2 * vp[k] + (1.0f - beta2) * gr * gr;
+                const float denom = sqrtf(vp[k]) * inv_sqrt_bc2 + eps;
+                pp[k] -= step_size * (mp[k] / denom);
+            }
+            st_f4_hint(reinterpret_cast<float4*>(p) + i, pv, stream_pol);
+            st_f4_hint(reinterpret_cast<float4*>(m) + i, mv, stream_pol);
+            st_f4_hint(reinterpret_cast<float4*>(v) + i, vv, stream_pol);
+            reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ph) {
+                uint2 h;
+                h.x = pack_half2(pv.x, pv.y);
+                h.y = pack_half2(pv.z, pv.w);
+                st_u2_hint(reinterpret_cast<uint2*>(ph) + i, h, keep_pol);
+            }
+        }
+        stage = (stage + 1) % ADAM_STAGES;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    // tail (n % 4 elements)
+    if (blockIdx.x == 0) {
+        for (int64_t i = (n4 << 2) + tid; i < n; i += ADAM_THREADS) {
+            const float gr = g[i] * grad_mul;
+            m[i] = beta1 * m[i] + (1.0f - beta1) * gr;
+            v[i] = beta2 * v[i] + (1.0f - beta2) * gr * gr;
+            p[i] -= step_size * (m[i] / (sqrtf(v[i]) * inv_sqrt_bc2 + eps));
+            g[i] = 0.f;
+            if (ph) ph[i] = __float2half_rn(p[i]);
+        }
+    }
+}
+
 __global__ void k_step_inc(int* step) { *step += 1; }
 
 extern "C" int ngp_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, uint16_t* params_half, int64_t n,
@@ -546,13 +629,33 @@ extern "C" int ngp_adam_step(float* params, float* grads, float* exp_avg, float*
         return NGP_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     if (n > 0) {
-        // 3 resident blocks per SM are enough to saturate HBM and leave room for the next step's march, which a
-        // trainer overlaps with this kernel on another stream
-        int grid = ngp_div_up((n >> 2) + 1, 256);
-        const int cap = ngp_sm_count() * 3;
-        if (grid > cap) grid = cap;
-        k_adam<<<grid, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, (__half*)params_half, n, lr_dev, step_dev, beta1, beta2,
-                                      eps, grad_mul);
+        // NGP_ADAM_VARIANT (env, read once): 0 = register stream (default), 1 = shared-memory staged stream. Measured inside the
+        // pipelined step on B200: 0.378 ms/step with 0 (2 blocks/SM; 3 -> 0.394, 4 -> 0.390, 1 -> 0.411) vs 0.393 with 1.
+        static int variant = -1;
+        if (variant < 0) {
+            const char* e = getenv("NGP_ADAM_VARIANT");
+            variant = e ? atoi(e) : 0;
+        }
+        if (variant == 1) {
+            const size_t smem = (size_t)ADAM_STAGES * 4 * ADAM_THREADS * sizeof(float4);
+            static bool attr_set = false;
+            if (!attr_set) {
+                NGP_CUDA(cudaFuncSetAttribute(k_adam_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr_set = true;
+            }
+            int grid = ngp_div_up((n >> 2) + 1, ADAM_THREADS);
+            if (grid > ngp_sm_count()) grid = ngp_sm_count();
+            k_adam_staged<<<grid, ADAM_THREADS, smem, st>>>(params, grads, exp_avg, exp_avg_sq, (__half*)params_half, n, lr_dev,
+                                                            step_dev, beta1, beta2, eps, grad_mul);
+        } else {
+            // 2 resident blocks per SM (two 64-byte groups per thread in flight) saturate HBM and leave registers for the
+            // next step's march, which a trainer overlaps with this kernel on another stream
+            int grid = ngp_div_up((n >> 2) + 1, 256);
+            const int cap = ngp_sm_count() * 2;
+            if (grid > cap) grid = cap;
+            k_adam<<<grid, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, (__half*)params_half, n, lr_dev, step_dev, beta1,
+                                          beta2, eps, grad_mul);
+        }
         NGP_CHECK_LAUNCH();
     }
     if (increment_step) {
