@@ -91,3 +91,13 @@ def test_ops_fail_loudly_without_gpu_or_library(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libngp_b200.so")
     with pytest.raises(RuntimeError):
         _lib.lib()
+
+
+def test_graft_entry_build_runs_on_cpu():
+    """the driver's "does it build" check: __graft_entry__.build() compiles (cached) and imports everything without a GPU"""
+    import importlib
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    entry = importlib.import_module("__graft_entry__")
+    entry.build()
