@@ -22,7 +22,7 @@ extern "C" {
 #define NGP_MAX_LEVELS 16
 #define NGP_ABI_VERSION 2
 
-int ngp_abi_version(void);
+int ngp_abi_version(void); /* == NGP_ABI_VERSION of the header the caller was built against */
 
 /* ----------------------------------------------------------------------------------------------
  * The twelve vren operators
@@ -110,14 +110,17 @@ typedef struct {
     float scale[NGP_MAX_LEVELS];
 } NgpGridMeta;
 
-/* Host-side: level table of the hash grid (no GPU needed). Returns total entries, 0 on bad input. */
+/* Host-side: level table of the hash grid (no GPU needed) for the encoding config the reference builds at
+ * models/networks.py:32-33,39-49 (L, F=2, log2_T, N_min, b = exp(log(2048*scale/N_min)/(L-1))). Returns total entries,
+ * 0 on bad input. */
 uint32_t ngp_grid_meta(int n_levels, int log2_hashmap_size, int base_resolution, float per_level_scale,
                        NgpGridMeta* out);
 
 #define NGP_DENSITY_MLP_PARAMS 3072 /* 64*32 + 16*64 */
 #define NGP_RGB_MLP_PARAMS 7168     /* 64*32 + 64*64 + 16*64 */
 
-/* fp32 -> fp16 working copy of a parameter vector (tinycudann casts its fp32 params every forward). */
+/* fp32 -> fp16 working copy of a parameter vector (the tinycudann modules of models/networks.py:36-77 keep one flat fp32
+ * `params` and cast it to fp16 on every forward). */
 int ngp_cast_params(const float* src, uint16_t* dst_half, int64_t n, void* stream);
 
 typedef struct {
@@ -155,7 +158,8 @@ int ngp_net_forward(const NgpNet* net, const NgpSamples* smp, int want_rgb, floa
                     uint16_t* h_out /* optional fp16 (n,16) */, void* feat_save /* 16-B aligned */, void* stream);
 
 size_t ngp_net_backward_workspace(int64_t n); /* 64 B per sample: feature gradients [level][sample] */
-/* Fused backward: recomputes the MLP activations from feat_save (or by re-gathering when NULL),
+/* Fused backward of NGP.forward (what autograd runs through models/networks.py:132-153 and TruncExp.backward,
+ * models/custom_functions.py:168-173): recomputes the MLP activations from feat_save (or by re-gathering when NULL),
  * back-propagates dL/dsigmas (n) and dL/drgbs (n,3), accumulates
  *   grad_enc (fp32, same layout as xyz_encoder.params) and grad_rgb (fp32, 7168)   with atomics (+=).
  * loss_scale (device float*, optional) is the power-of-two the fp16 gradient operands are scaled by
@@ -189,7 +193,8 @@ int ngp_mlp_rgb_backward(const uint16_t* rgb_params_h, const uint16_t* x_half, c
 int ngp_enc_backward(const NgpNet* net, const NgpSamples* smp, const float* dL_dh, const void* feat_save,
                      const float* loss_scale, float* grad_enc, void* workspace, size_t workspace_bytes, void* stream);
 
-/* loss_scale helper: *scale_out = 2^floor(log2(256 / max(|dL_dsigmas*sigma'|, |dL_drgbs|))) (1 if all zero). */
+/* loss_scale helper (the role PL's GradScaler plays for Trainer(precision=16), train.py:274, and tinycudann's fixed
+ * loss_scale = 128): *scale_out = 2^floor(log2(256 / max(|dL_dsigmas*sigma'|, |dL_drgbs|))) (1 if all zero). */
 int ngp_grad_scale(const float* dL_dsigmas, const float* sigmas, const float* dL_drgbs, int64_t n,
                    float* scratch /* 1 float */, float* scale_out, void* stream);
 
@@ -246,9 +251,10 @@ typedef struct {
     size_t bwd_workspace_bytes;
 } NgpTrainBuffers;
 
-size_t ngp_train_scan_temp_bytes(int n_rays);
+size_t ngp_train_scan_temp_bytes(int n_rays); /* NgpTrainBuffers.scan_temp size */
 
-/* forward: fills per-ray rgb/opacity/depth (+ws) and everything the backward needs */
+/* forward = __render_rays_train (models/rendering.py:121-163) incl. the AABB test and near clamp of render() (:25-29):
+ * fills per-ray rgb/opacity/depth (+ws) and everything the backward needs */
 int ngp_render_train_fwd(const NgpNet* net, const NgpTrainCfg* cfg, const NgpTrainBuffers* buf, void* stream);
 /* its two halves: _march (AABB + march + scan + compaction; independent of the weights, so it may overlap the
  * optimiser of the previous step) and _net (network + compositing). _fwd == _march then _net. */
@@ -262,8 +268,9 @@ int ngp_render_train_net(const NgpNet* net, const NgpTrainCfg* cfg, const NgpTra
 int ngp_render_train_step(const NgpNet* net, const NgpTrainCfg* cfg, const NgpTrainBuffers* b, const float* rgb_gt,
                           float* grad_enc, float* grad_rgb, void* stream);
 
-/* backward from per-ray gradients (dL_ddepth / dL_dws may be NULL = 0); accumulates (+=) into the
- * fp32 gradient vectors laid out like the parameter vectors. */
+/* backward of the above from per-ray gradients = VolumeRenderer.backward (models/custom_functions.py:148-159) followed by
+ * the network backward (dL_ddepth / dL_dws may be NULL = 0); accumulates (+=) into the fp32 gradient vectors laid out like
+ * the parameter vectors. */
 int ngp_render_train_bwd(const NgpNet* net, const NgpTrainCfg* cfg, const NgpTrainBuffers* buf,
                          const float* dL_drgb, const float* dL_dopacity, const float* dL_ddepth, const float* dL_dws,
                          float* grad_enc, float* grad_rgb, void* stream);
@@ -284,7 +291,8 @@ int ngp_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq
                   const float* lr_dev, int32_t* step_dev, float beta1, float beta2, float eps, float grad_mul,
                   int increment_step, void* stream);
 
-/* Data-parallel optimiser step FUSED with its collective over NVLink peer memory (N ranks of one node):
+/* Data-parallel optimiser step FUSED with its collective over NVLink peer memory (N ranks of one node); replaces the DDP
+ * gradient all-reduce (train.py:269-272, DDPPlugin) + FusedAdam.step (train.py:131-137) of the reference:
  * rank `rank` reduces its 1/N shard of the gradient directly from every rank's gradient buffer (P2P loads),
  * applies Adam (mean gradient, same semantics as ngp_adam_step) to that shard of params / exp_avg /
  * exp_avg_sq, and stores the shard's new fp16 parameters into every rank's working copy (P2P stores).
@@ -332,7 +340,7 @@ typedef struct {
     int64_t max_round_samples;  /* capacity of the per-round sample buffers, shared fairly by the alive rays */
 } NgpInferCfg;
 
-size_t ngp_render_infer_workspace(int n_rays, int64_t max_round_samples);
+size_t ngp_render_infer_workspace(int n_rays, int64_t max_round_samples); /* workspace of ngp_render_infer */
 /* Runs rounds [first_round, first_round+n_rounds) of the wavefront (first_round == 0 initialises; finish != 0
  * adds the background and writes total_samples). Per round every alive ray takes up to
  * min(2,2,4,4,...,64 schedule, max_round_samples / n_alive) samples. alive_count_out (device int32*, optional)
