@@ -1,113 +1,129 @@
-"""The five torch.autograd.Function wrappers of reference models/custom_functions.py, same class names
-and `.apply` argument order, running on libngp_b200.so.
+"""Autograd entry points of the operator-level API.
 
-    RayAABBIntersector   reference custom_functions.py:8-29
-    RaySphereIntersector reference custom_functions.py:32-52
-    RayMarcher           reference custom_functions.py:55-112
-    VolumeRenderer       reference custom_functions.py:115-159
-    TruncExp             reference custom_functions.py:162-173
+A reference user calls five ``torch.autograd.Function``s from ``models/custom_functions.py``; the same five names with the
+same ``.apply`` argument order are defined here on top of ``ngp_pl_b200.vren`` (libngp_b200.so):
+
+    ================================  =========================================
+    RayAABBIntersector.apply(o, d, center, half_size, max_hits)   reference custom_functions.py:8-29
+    RaySphereIntersector.apply(o, d, center, radii, max_hits)     reference custom_functions.py:32-52
+    RayMarcher.apply(o, d, hits_t, bitfield, cascades, scale, exp_step_factor, grid_size, max_samples)   :55-112
+    VolumeRenderer.apply(sigmas, rgbs, deltas, ts, rays_a, T_threshold)                                  :115-159
+    TruncExp.apply(x)                                                                                    :162-173
+    ================================  =========================================
+
+Like the reference's wrappers they run the native operators in fp32 whatever the autocast state is.
 """
 import torch
 from torch.amp import custom_bwd, custom_fwd
 
 from .. import vren
 
-
-class RayAABBIntersector(torch.autograd.Function):
-    """rays (N,3) x boxes (V,3) -> hits_cnt (N), hits_t (N,max_hits,2) near-to-far (-1: no hit),
-    hits_voxel_idx (N,max_hits)."""
-
-    @staticmethod
-    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, rays_o, rays_d, center, half_size, max_hits):
-        return tuple(vren.ray_aabb_intersect(rays_o, rays_d, center, half_size, max_hits))
+_fp32_forward = custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+_amp_backward = custom_bwd(device_type="cuda")
 
 
-class RaySphereIntersector(torch.autograd.Function):
-    @staticmethod
-    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, rays_o, rays_d, center, radii, max_hits):
-        return tuple(vren.ray_sphere_intersect(rays_o, rays_d, center, radii, max_hits))
+def _intersector(operator_name, summary):
+    """Function class for a ray / primitive intersection operator: no gradient, three outputs
+    (hit count (N), hit intervals (N, max_hits, 2) sorted near to far with -1 = no hit, primitive index (N, max_hits))."""
+
+    class _Intersect(torch.autograd.Function):
+        __doc__ = summary
+
+        @staticmethod
+        @_fp32_forward
+        def forward(ctx, rays_o, rays_d, center, extent, max_hits):
+            hit_cnt, hits_t, hits_idx = getattr(vren, operator_name)(rays_o, rays_d, center, extent, max_hits)
+            return hit_cnt, hits_t, hits_idx
+
+    return _Intersect
+
+
+RayAABBIntersector = _intersector("ray_aabb_intersect", "Rays (N,3) against axis-aligned boxes given by centre (V,3) and half size (V,3).")
+RayAABBIntersector.__name__ = RayAABBIntersector.__qualname__ = "RayAABBIntersector"
+RaySphereIntersector = _intersector("ray_sphere_intersect", "Rays (N,3) against spheres given by centre (V,3) and radius (V).")
+RaySphereIntersector.__name__ = RaySphereIntersector.__qualname__ = "RaySphereIntersector"
+
+
+def _sum_per_ray(per_sample, rays_a):
+    """(S, C) per-sample values -> (N, C) per-ray sums; rays_a rows are [ray, first sample, count] in ray order and the samples
+    of a ray are contiguous (the reference uses torch_scatter.segment_csr on the same offsets)."""
+    n_rays = rays_a.shape[0]
+    owner = torch.repeat_interleave(torch.arange(n_rays, device=per_sample.device), rays_a[:, 2])
+    return torch.zeros(n_rays, per_sample.shape[1], device=per_sample.device, dtype=per_sample.dtype).index_add_(0, owner, per_sample)
 
 
 class RayMarcher(torch.autograd.Function):
-    """March rays through the occupancy bitfield.
+    """Occupancy-grid march of a batch of rays (training): every ray contributes the sample positions that fall into
+    occupied cells between its entry and exit of the scene box, with a random sub-step start offset.
 
-    Inputs : rays_o, rays_d (N,3); hits_t (N,2); density_bitfield (C*G^3/8) uint8; cascades; scale;
-             exp_step_factor; grid_size; max_samples
-    Outputs: rays_a (N,3) [ray_idx,start_idx,N_samples]; xyzs, dirs (S,3); deltas, ts (S); total_samples
-    An optional `noise` attribute (class-level, (N,) tensor) replaces the internally drawn start
-    jitter -- used by parity tests to march identical rays with the reference kernels.
+    Returns ``rays_a`` (N,3) int64 rows [ray index, first sample, sample count], ``xyzs``/``dirs`` (S,3), ``deltas``/``ts`` (S)
+    and the total S (a 0-d tensor). Gradients flow to ``rays_o`` / ``rays_d`` (x = o + t d), as in the reference.
+    ``RayMarcher.noise_override`` (an (N,) tensor, class attribute) replaces the internally drawn start offsets -- the parity
+    tests use it to march identical rays through the reference's kernels.
     """
     noise_override = None
 
     @staticmethod
-    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    @_fp32_forward
     def forward(ctx, rays_o, rays_d, hits_t, density_bitfield, cascades, scale, exp_step_factor, grid_size, max_samples):
-        if RayMarcher.noise_override is not None:
-            noise = RayMarcher.noise_override
-        else:
-            noise = torch.rand_like(rays_o[:, 0])
+        jitter = RayMarcher.noise_override
+        if jitter is None:
+            jitter = torch.rand(rays_o.shape[0], device=rays_o.device, dtype=rays_o.dtype)
         rays_a, xyzs, dirs, deltas, ts, counter = vren.raymarching_train(
-            rays_o, rays_d, hits_t, density_bitfield, cascades, scale, exp_step_factor, noise, grid_size, max_samples)
-        total_samples = counter[0]
-        n = int(total_samples)  # the one host sync of this (unfused) API, as in the reference (:91-96)
-        xyzs, dirs, deltas, ts = xyzs[:n], dirs[:n], deltas[:n], ts[:n]
-        ctx.save_for_backward(rays_a, ts)
-        return rays_a, xyzs, dirs, deltas, ts, total_samples
+            rays_o, rays_d, hits_t, density_bitfield, cascades, scale, exp_step_factor, jitter, grid_size, max_samples)
+        total = counter[0]
+        used = int(total)  # the operator-level API sizes its outputs on the host, like the reference (:91-96): one sync
+        ctx.save_for_backward(rays_a, ts[:used])
+        return rays_a, xyzs[:used], dirs[:used], deltas[:used], ts[:used], total
 
     @staticmethod
-    @custom_bwd(device_type="cuda")
-    def backward(ctx, dL_drays_a, dL_dxyzs, dL_ddirs, dL_ddeltas, dL_dts, dL_dtotal_samples):
+    @_amp_backward
+    def backward(ctx, g_rays_a, g_xyzs, g_dirs, g_deltas, g_ts, g_total):
         rays_a, ts = ctx.saved_tensors
-        # per-ray sums of the per-sample gradients (the reference uses torch_scatter.segment_csr)
-        n_rays = rays_a.shape[0]
-        seg = torch.repeat_interleave(torch.arange(n_rays, device=ts.device), rays_a[:, 2])
-        dL_drays_o = torch.zeros(n_rays, 3, device=ts.device, dtype=dL_dxyzs.dtype).index_add_(0, seg, dL_dxyzs)
-        dL_drays_d = torch.zeros(n_rays, 3, device=ts.device, dtype=dL_dxyzs.dtype).index_add_(
-            0, seg, dL_dxyzs * ts[:, None] + dL_ddirs)
-        # rows of rays_a are ordered by ray index here, so row order == ray order
-        return dL_drays_o, dL_drays_d, None, None, None, None, None, None, None
+        # x = o + t d and dirs = d per sample  =>  dL/do = sum g_x ,  dL/dd = sum (t g_x + g_dirs)   over the ray's samples
+        grad_o = _sum_per_ray(g_xyzs, rays_a)
+        grad_d = _sum_per_ray(g_xyzs * ts.unsqueeze(1) + g_dirs, rays_a)
+        return (grad_o, grad_d) + (None,) * 7
 
 
 class VolumeRenderer(torch.autograd.Function):
-    """Ragged front-to-back compositing (training).
+    """Front-to-back alpha compositing of ragged per-ray sample lists (training).
 
-    Inputs : sigmas (S); rgbs (S,3); deltas (S); ts (S); rays_a (N,3); T_threshold
-    Outputs: total_samples (scalar); opacity (N); depth (N); rgb (N,3); ws (S)
+    sigmas (S), rgbs (S,3), deltas (S), ts (S), rays_a (N,3), T_threshold -> total composited samples (0-d), opacity (N),
+    depth (N), rgb (N,3), per-sample weights ws (S). Gradients flow to sigmas and rgbs.
     """
 
     @staticmethod
-    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    @_fp32_forward
     def forward(ctx, sigmas, rgbs, deltas, ts, rays_a, T_threshold):
-        total_samples, opacity, depth, rgb, ws = vren.composite_train_fw(
-            sigmas.contiguous(), rgbs.contiguous(), deltas.contiguous(), ts.contiguous(), rays_a, T_threshold)
-        ctx.save_for_backward(sigmas, rgbs, deltas, ts, rays_a, opacity, depth, rgb, ws)
+        args = [t.contiguous() for t in (sigmas, rgbs, deltas, ts)]
+        per_ray_count, opacity, depth, rgb, ws = vren.composite_train_fw(*args, rays_a, T_threshold)
         ctx.T_threshold = T_threshold
-        return total_samples.sum(), opacity, depth, rgb, ws
+        ctx.save_for_backward(*args, rays_a, opacity, depth, rgb, ws)
+        return per_ray_count.sum(), opacity, depth, rgb, ws
 
     @staticmethod
-    @custom_bwd(device_type="cuda")
-    def backward(ctx, dL_dtotal_samples, dL_dopacity, dL_ddepth, dL_drgb, dL_dws):
+    @_amp_backward
+    def backward(ctx, g_count, g_opacity, g_depth, g_rgb, g_ws):
         sigmas, rgbs, deltas, ts, rays_a, opacity, depth, rgb, ws = ctx.saved_tensors
-        dL_dsigmas, dL_drgbs = vren.composite_train_bw(
-            dL_dopacity.contiguous(), dL_ddepth.contiguous(), dL_drgb.contiguous(), dL_dws.contiguous(),
-            sigmas.contiguous(), rgbs.contiguous(), ws, deltas.contiguous(), ts.contiguous(), rays_a,
-            opacity, depth, rgb, ctx.T_threshold)
-        return dL_dsigmas, dL_drgbs, None, None, None, None
+        g_sigmas, g_rgbs = vren.composite_train_bw(
+            g_opacity.contiguous(), g_depth.contiguous(), g_rgb.contiguous(), g_ws.contiguous(),
+            sigmas, rgbs, ws, deltas, ts, rays_a, opacity, depth, rgb, ctx.T_threshold)
+        return g_sigmas, g_rgbs, None, None, None, None
 
 
 class TruncExp(torch.autograd.Function):
-    """exp with a clamped backward (reference custom_functions.py:162-173)."""
+    """exp(x) whose derivative is evaluated at clamp(x, -15, 15): the density activation (a runaway pre-activation cannot
+    blow the gradient up)."""
 
     @staticmethod
-    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    @_fp32_forward
     def forward(ctx, x):
         ctx.save_for_backward(x)
-        return torch.exp(x)
+        return x.exp()
 
     @staticmethod
-    @custom_bwd(device_type="cuda")
-    def backward(ctx, dL_dout):
-        x = ctx.saved_tensors[0]
-        return dL_dout * torch.exp(x.clamp(-15, 15))
+    @_amp_backward
+    def backward(ctx, g_out):
+        (x,) = ctx.saved_tensors
+        return g_out * torch.clamp(x, min=-15.0, max=15.0).exp()
