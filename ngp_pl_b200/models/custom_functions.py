@@ -73,8 +73,9 @@ class RayMarcher(torch.autograd.Function):
             rays_o, rays_d, hits_t, density_bitfield, cascades, scale, exp_step_factor, jitter, grid_size, max_samples)
         total = counter[0]
         used = int(total)  # the operator-level API sizes its outputs on the host, like the reference (:91-96): one sync
-        ctx.save_for_backward(rays_a, ts[:used])
-        return rays_a, xyzs[:used], dirs[:used], deltas[:used], ts[:used], total
+        ts_used = ts[:used]
+        ctx.save_for_backward(rays_a, ts_used)
+        return rays_a, xyzs[:used], dirs[:used], deltas[:used], ts_used, total
 
     @staticmethod
     @_amp_backward
