@@ -35,6 +35,12 @@ def _net_struct(model):
     return net, (enc_h, rgb_h)
 
 
+def need_cuda(t, what):
+    """there is no CPU path: fail like the reference's TORCH_CHECK(is_cuda) (models/csrc/include/utils.h:4-6)"""
+    if not t.is_cuda:
+        raise RuntimeError("ngp_pl_b200: %s needs CUDA tensors (got %s); there is no CPU or PyTorch fallback" % (what, t.device))
+
+
 def _samples_struct(x, d):
     s = _lib.NgpSamples()
     s.xyzs = x.data_ptr()
@@ -263,6 +269,7 @@ class NGP(nn.Module):
     # ------------------------------------------------------------------ network evaluation
     @torch.no_grad()
     def _density_nograd(self, x):
+        need_cuda(x, "NGP.density")
         x = x.contiguous().float()
         n = x.shape[0]
         with torch.cuda.device(x.device):
@@ -286,6 +293,7 @@ class NGP(nn.Module):
         (reference networks.py:132-153)."""
         if self.rgb_act == 'None' and not kwargs.get('output_radiance', False):
             raise NotImplementedError("HDR tonemapper path (use_exposure) is outside the hot path")
+        need_cuda(x, "NGP.forward")
         sig, rgb = _NGPForward.apply(x, d, self.xyz_encoder.params, self.rgb_net.params, self)
         if self.rgb_act == 'None':
             from .custom_functions import TruncExp

@@ -71,7 +71,8 @@ class Encoding(nn.Module):
         self.params = nn.Parameter(torch.zeros(0, dtype=torch.float32))
 
     def forward(self, x):
-        from .models.networks import sh_encode
+        from .models.networks import need_cuda, sh_encode
+        need_cuda(x, "tcnn.Encoding")
         return sh_encode(x)
 
 
@@ -114,7 +115,8 @@ class NetworkWithInputEncoding(nn.Module):
 
     def forward(self, x):
         """x in [0,1]^3 (N,3) -> fp16 (N,16). Differentiable w.r.t. params."""
-        from .models.networks import _DensityFeatures
+        from .models.networks import _DensityFeatures, need_cuda
+        need_cuda(x, "tcnn.NetworkWithInputEncoding")
         return _DensityFeatures.apply(x, self.params, self)
 
 
@@ -145,5 +147,6 @@ class Network(nn.Module):
         return self._half.get(self.params)
 
     def forward(self, x):
-        from .models.networks import _RgbMlp
+        from .models.networks import _RgbMlp, need_cuda
+        need_cuda(x, "tcnn.Network")
         return _RgbMlp.apply(x, self.params, self)
