@@ -52,6 +52,22 @@ def zero_shard(n_params, world_size, rank):
     return lo, hi, n_pad
 
 
+def zero_exchange(G_full, G_shard, Ph_full, shard_bounds, rank, world_size, process_group, adam_on_shard):
+    """One optimiser step of the "zero" mode on the padded flat buffers: reduce_scatter(SUM) of the gradient into this rank's
+    shard, clear the local gradient, `adam_on_shard(lo, hi, G_shard)` updates the owned parameters [lo, hi) (and writes their
+    slice of the fp16 working copy Ph_full), all_gather of the working copy. Pure orchestration: the GPU trainer passes the
+    CUDA Adam kernel, the gloo test a torch one."""
+    import torch.distributed as dist
+    lo, hi, n_pad = shard_bounds
+    shard = n_pad // world_size
+    dist.reduce_scatter_tensor(G_shard, G_full, op=dist.ReduceOp.SUM, group=process_group)
+    G_full.zero_()
+    if hi > lo:
+        adam_on_shard(lo, hi, G_shard)
+    mine = rank * shard  # (lo is clamped to n_params when a shard is all padding)
+    dist.all_gather_into_tensor(Ph_full, Ph_full[mine:mine + shard], group=process_group)
+
+
 def shard_range(n_items, world_size, rank):
     """contiguous shard [lo, hi) of n_items (test views / image rows) for `rank`; sizes differ by at most one"""
     base, extra = divmod(n_items, world_size)
@@ -360,18 +376,13 @@ class Trainer:
 
     def _optimizer_step_zero(self):
         """reduce_scatter(grad) -> Adam on the owned shard (writes its slice of the fp16 copy) -> all_gather(fp16 copy)"""
-        import torch.distributed as dist
-        lo, hi, n_pad = self._zero
-        shard = n_pad // self.world_size
-        dist.reduce_scatter_tensor(self.G_shard, self.G_full, op=dist.ReduceOp.SUM, group=self.pg)
-        self.G_full.zero_()
-        if hi > lo:
-            rc = _lib.lib().ngp_adam_step(self.P[lo:].data_ptr(), self.G_shard.data_ptr(), self.M[lo:].data_ptr(),
+        def adam_on_shard(lo, hi, g_shard):
+            rc = _lib.lib().ngp_adam_step(self.P[lo:].data_ptr(), g_shard.data_ptr(), self.M[lo:].data_ptr(),
                                           self.V[lo:].data_ptr(), self.Ph_full[lo:].data_ptr(), hi - lo, self.lr_dev.data_ptr(),
                                           self.step_dev.data_ptr(), self.betas[0], self.betas[1], self.eps,
                                           1.0 / self.world_size, 1, self._st())
             _lib.check(rc, "adam_step")
-        dist.all_gather_into_tensor(self.Ph_full, self.Ph_full[lo:lo + shard], group=self.pg)
+        zero_exchange(self.G_full, self.G_shard, self.Ph_full, self._zero, self.rank, self.world_size, self.pg, adam_on_shard)
 
     def _optimizer_step_p2p(self):
         """barrier -> fused reduce-scatter + sharded Adam + all-gather over NVLink -> barrier -> clear own gradients"""

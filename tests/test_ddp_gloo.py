@@ -101,3 +101,56 @@ def test_zero_shards_partition_the_parameters():
                 assert lo == min(r * (n_pad // world), n)
                 covered += hi - lo
             assert covered == n
+
+
+def _zero_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ngp_pl_b200.trainer import zero_exchange, zero_shard
+    n = 1003  # not a multiple of 4 * world: exercises the padding
+    g = torch.Generator().manual_seed(7)
+    P0 = torch.randn(n, generator=g)
+    grads = [torch.randn(n, generator=g) for _ in range(world)]  # every rank's local gradient (known to all, for the check)
+    lo, hi, n_pad = zero_shard(n, world, rank)
+    P, M, V = P0.clone(), torch.zeros(n), torch.zeros(n)
+    G_full = torch.zeros(n_pad)
+    G_full[:n] = grads[rank]
+    G_shard = torch.zeros(n_pad // world)
+    Ph_full = torch.zeros(n_pad, dtype=torch.float16)
+    Ph_full[:n] = P0.half()
+    lr, b1, b2, eps = 1e-2, 0.9, 0.999, 1e-15
+
+    def adam_on_shard(lo_, hi_, g_shard):  # torch stand-in for ngp_adam_step(grad_mul = 1/world) on the owned slice
+        gm = g_shard[:hi_ - lo_] / world
+        M[lo_:hi_] = b1 * M[lo_:hi_] + (1 - b1) * gm
+        V[lo_:hi_] = b2 * V[lo_:hi_] + (1 - b2) * gm * gm
+        P[lo_:hi_] -= lr / (1 - b1) * M[lo_:hi_] / (V[lo_:hi_].sqrt() / (1 - b2) ** 0.5 + eps)
+        Ph_full[lo_:hi_] = P[lo_:hi_].half()
+        g_shard.zero_()
+    zero_exchange(G_full, G_shard, Ph_full, (lo, hi, n_pad), rank, world, None, adam_on_shard)
+    assert float(G_full.abs().max()) == 0.0  # local gradient cleared for the next step
+    torch.save({"Ph": Ph_full[:n].clone(), "P_shard": P[lo:hi].clone(), "lo": lo, "hi": hi}, out % rank)
+    dist.destroy_process_group()
+
+
+def test_zero_mode_exchange_equals_allreduce_plus_full_adam(tmp_path):
+    """reduce_scatter -> Adam on the owned shard -> all_gather(fp16 copy) gives every rank the parameters that an
+    all_reduce + full Adam step gives (first step, mean gradient)"""
+    world = 2
+    out = str(tmp_path / "zero_r%d.pt")
+    mp.spawn(_zero_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    n = 1003
+    g = torch.Generator().manual_seed(7)
+    P0 = torch.randn(n, generator=g)
+    grads = [torch.randn(n, generator=g) for _ in range(world)]
+    ref = P0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-2, betas=(0.9, 0.999), eps=1e-15)
+    ref.grad = sum(grads) / world
+    opt.step()
+    res = [torch.load(out % r) for r in range(world)]
+    assert torch.equal(res[0]["Ph"], res[1]["Ph"])  # every rank holds the complete fp16 working copy
+    assert torch.allclose(res[0]["Ph"].float(), ref.detach().half().float(), atol=2e-3, rtol=2e-3)
+    for r in res:  # fp32 master values of the owned shard
+        assert torch.allclose(r["P_shard"], ref.detach()[r["lo"]:r["hi"]], rtol=1e-5, atol=1e-6)
+    assert res[0]["lo"] == 0 and res[0]["hi"] == res[1]["lo"] and res[1]["hi"] == n
