@@ -115,6 +115,19 @@ def march_train(rays_o, rays_d, hits_t, bits, cascades, scale, esf, noise, grid_
     return rays_a, xyzs, dirs, deltas, ts
 
 
+def march_probe(ray_o, ray_d, bits, cascades, scale, esf, dt_scale, grid_size, max_samples, t):
+    """per-point part of one marcher visit for parameters t (n,) of ONE ray -> occ (n) int32, dt (n), t_target (n)"""
+    o, d, tt = _f(ray_o).reshape(3), _f(ray_d).reshape(3), _f(t).reshape(-1)
+    bits = np.ascontiguousarray(bits, dtype=np.uint8)
+    n = tt.shape[0]
+    occ = np.zeros(n, np.int32)
+    dt = np.zeros(n, np.float32)
+    tgt = np.zeros(n, np.float32)
+    lib().oracle_march_probe(_ptr(o), _ptr(d), _ptr(bits), C.c_int(cascades), C.c_float(scale), C.c_float(esf), C.c_float(dt_scale),
+                             C.c_int(grid_size), C.c_int(max_samples), _ptr(tt), C.c_int(n), _ptr(occ), _ptr(dt), _ptr(tgt))
+    return occ, dt, tgt
+
+
 def march_test(rays_o, rays_d, hits_t, alive, bits, cascades, scale, esf, grid_size, max_samples, N_samples):
     """hits_t (n_rays,2) float32 array is modified in place. -> xyzs, dirs, deltas, ts, n_eff"""
     o, d = _f(rays_o), _f(rays_d)
