@@ -20,9 +20,15 @@ extern "C" {
 #endif
 
 #define NGP_MAX_LEVELS 16
-#define NGP_ABI_VERSION 2
+#define NGP_ABI_VERSION 3
 
 int ngp_abi_version(void); /* == NGP_ABI_VERSION of the header the caller was built against */
+
+/* Number of kernel launches this library has issued in this process so far -- eager launches and launches recorded
+ * into a CUDA graph under stream capture alike (cub's kernels launched on its behalf included; a graph REPLAY does not
+ * pass through the library, so a caller multiplies a graph's recorded count by its replays). Evidence for bench.py's
+ * `gpu_launches`; no reference counterpart. */
+unsigned long long ngp_launch_count(void);
 
 /* ----------------------------------------------------------------------------------------------
  * The twelve vren operators
@@ -249,6 +255,8 @@ typedef struct {
     size_t scan_temp_bytes;
     void* bwd_workspace;          /* ngp_net_backward_workspace(max_total_samples) bytes */
     size_t bwd_workspace_bytes;
+    const float* bg_dev;          /* optional device float[3]: background colour of THIS batch, overrides cfg.bg (the
+                                     reference's random_bg draws one colour per training batch, rendering.py:153-161) */
 } NgpTrainBuffers;
 
 size_t ngp_train_scan_temp_bytes(int n_rays); /* NgpTrainBuffers.scan_temp size */
@@ -303,6 +311,24 @@ int ngp_adam_step_p2p(int world, int rank, const uint64_t* peer_grads, float* pa
                       const uint64_t* peer_params_half, int64_t n, const float* lr_dev, int32_t* step_dev, float beta1,
                       float beta2, float eps, int increment_step, void* stream);
 
+/* The same exchange as ONE self-synchronising, CUDA-graph-capturable kernel (no host-side barriers):
+ *   start barrier (flag words in symmetric memory) -> reduce-scatter + Adam on the owned shard + all-gather of the
+ *   new fp16 parameters -> end barrier; the kernel ends only when this rank's working copy is complete and every
+ *   peer is done reading this rank's gradients.
+ * peer_flags: HOST array of `world` device addresses of each rank's flag block (>= 32 uint32, symmetric memory,
+ * zero-initialised once, never reset). mc_grads / mc_params_half: NVLS multicast aliases of the gradient buffer /
+ * the fp16 working copy (0 = none): with them the reduction is one multimem.ld_reduce and the all-gather one
+ * multimem.st per 16 bytes (the switch sums / replicates; summation order then differs from NCCL's).
+ * zero_buf (may be NULL): a LOCAL fp32 buffer of n elements cleared inside the kernel -- the gradient buffer the
+ * NEXT step accumulates into; gradient buffers must alternate between steps, the buffer being reduced is left
+ * untouched. sync: >= 4 uint32 of local device memory, zero-initialised once ([2] != 0 afterwards = a peer never
+ * arrived: timeout). n must be a multiple of 4. */
+int ngp_adam_step_fused(int world, int rank, const uint64_t* peer_grads, const uint64_t* peer_params_half,
+                        const uint64_t* peer_flags, uint64_t mc_grads, uint64_t mc_params_half, float* params,
+                        float* exp_avg, float* exp_avg_sq, int64_t n, float* zero_buf, uint32_t* sync,
+                        const float* lr_dev, int32_t* step_dev, float beta1, float beta2, float eps,
+                        int increment_step, void* stream);
+
 /* Batch assembly on the device (reference train.py:78-91 + datasets/ray_utils.py:46-70 + base.py:22-30):
  * rays_d = directions[pix] @ R^T, rays_o = c2w[:,3], rgb_gt = images[img, pix] / 255. */
 int ngp_gen_rays(const int64_t* img_idx, const int64_t* pix_idx, const float* poses /* (n_img,3,4) */,
@@ -320,9 +346,11 @@ int ngp_sample_rays(const float* poses, const float* directions, const uint8_t* 
 /* Occupancy-grid refresh on the device (reference networks.py:240-269 + :169-195), no host sync:
  * picks cells (all cells when warmup, else M uniform + M occupied per cascade), evaluates sigma at a
  * jittered point of each, grid = grid<0 ? grid : max(grid*decay, sigma), threshold = min(mean of
- * positive cells, density_threshold), packs the bitfield. workspace: see ngp_update_grid_workspace. */
+ * positive cells, density_threshold), packs the bitfield. With count_grid (networks.py:258-260, `erode`): per-cell
+ * decay = clamp(decay^(1/count), 0.1, 0.95). workspace: see ngp_update_grid_workspace. */
 size_t ngp_update_grid_workspace(int cascades, int grid_size);
 int ngp_update_density_grid(const NgpNet* net, float* density_grid /* (cascades, G^3) */, uint8_t* density_bitfield,
+                            const float* count_grid /* (cascades, G^3) camera coverage for `erode`, or NULL */,
                             int cascades, int grid_size, float scale, float density_threshold, int warmup, float decay,
                             uint32_t seed, void* workspace, size_t workspace_bytes, void* stream);
 

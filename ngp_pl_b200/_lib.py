@@ -9,7 +9,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libngp_b200.so")
-ABI_VERSION = 2  # NGP_ABI_VERSION in include/ngp_b200.h
+ABI_VERSION = 3  # NGP_ABI_VERSION in include/ngp_b200.h
 
 NGP_MAX_LEVELS = 16
 NGP_DENSITY_MLP_PARAMS = 3072
@@ -96,7 +96,8 @@ class NgpTrainBuffers(C.Structure):
         "rays_o", "rays_d", "noise", "density_bitfield",
         "stage_t", "stage_dt", "n_samples", "offsets", "counters", "rgb", "opacity", "depth",
         "ray_idx", "ts", "deltas", "sigmas", "rgbs", "ws", "dsigmas", "drgbs", "live_idx", "feat_save", "scalars",
-        "scan_temp")] + [("scan_temp_bytes", C.c_size_t), ("bwd_workspace", C.c_void_p), ("bwd_workspace_bytes", C.c_size_t)]
+        "scan_temp")] + [("scan_temp_bytes", C.c_size_t), ("bwd_workspace", C.c_void_p), ("bwd_workspace_bytes", C.c_size_t),
+                                  ("bg_dev", C.c_void_p)]
 
 
 _P = C.c_void_p
@@ -109,6 +110,7 @@ _sz = C.c_size_t
 # tests/test_abi.py checks header <-> table <-> library agreement.
 SIGNATURES = {
     "ngp_abi_version": (_i, []),
+    "ngp_launch_count": (C.c_ulonglong, []),
     "ngp_ray_aabb_intersect": (_i, [_P, _P, _P, _P, _i, _i, _i, _P, _P, _P, _P]),
     "ngp_ray_sphere_intersect": (_i, [_P, _P, _P, _P, _i, _i, _i, _P, _P, _P, _P]),
     "ngp_packbits": (_i, [_P, _i, _i64, _f, _P, _P, _P]),
@@ -145,13 +147,14 @@ SIGNATURES = {
     "ngp_nerf_loss_grad": (_i, [C.POINTER(NgpTrainCfg), C.POINTER(NgpTrainBuffers), _P, _P, _P, _P]),
     "ngp_adam_step": (_i, [_P, _P, _P, _P, _P, _i64, _P, _P, _f, _f, _f, _f, _i, _P]),
     "ngp_adam_step_p2p": (_i, [_i, _i, _P, _P, _P, _P, _P, _i64, _P, _P, _f, _f, _f, _i, _P]),
+    "ngp_adam_step_fused": (_i, [_i, _i, _P, _P, _P, C.c_uint64, C.c_uint64, _P, _P, _P, _i64, _P, _P, _P, _P, _f, _f, _f, _i, _P]),
     "ngp_gen_rays": (_i, [_P, _P, _P, _P, _P, _i64, _i, _P, _P, _P, _P]),
     "ngp_sample_rays": (_i, [_P, _P, _P, _i, _i64, _i, C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, _P]),
     "ngp_render_infer_workspace": (_sz, [_i, _i64]),
     "ngp_render_infer": (_i, [C.POINTER(NgpNet), C.POINTER(NgpInferCfg), _P, _P, _P, _P, _P, _P, _P, _i, _i, _i, _P,
                               _P, _sz, _P]),
     "ngp_update_grid_workspace": (_sz, [_i, _i]),
-    "ngp_update_density_grid": (_i, [C.POINTER(NgpNet), _P, _P, _i, _i, _f, _f, _i, _f, C.c_uint32, _P, _sz, _P]),
+    "ngp_update_density_grid": (_i, [C.POINTER(NgpNet), _P, _P, _P, _i, _i, _f, _f, _i, _f, C.c_uint32, _P, _sz, _P]),
 }
 
 _lib = None

@@ -10,8 +10,14 @@
 // or NGP_EINVAL (<0) for an argument the op cannot honour. Nothing allocates.
 #define NGP_EINVAL (-22)
 
+// process-wide count of the kernel launches this library has issued (eager launches and launches recorded into a CUDA
+// graph under capture alike; defined in network.cu, read through ngp_launch_count()). Host threads only.
+extern unsigned long long g_ngp_launch_count;
+#define NGP_COUNT_LAUNCHES(k) (__atomic_fetch_add(&g_ngp_launch_count, (unsigned long long)(k), __ATOMIC_RELAXED))
+
 #define NGP_CHECK_LAUNCH()                                   \
     do {                                                     \
+        NGP_COUNT_LAUNCHES(1);                               \
         cudaError_t _e = cudaGetLastError();                 \
         if (_e != cudaSuccess) return (int)_e;               \
     } while (0)

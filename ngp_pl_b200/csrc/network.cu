@@ -12,6 +12,9 @@
 
 extern "C" int ngp_abi_version(void) { return NGP_ABI_VERSION; }
 
+unsigned long long g_ngp_launch_count = 0;
+extern "C" unsigned long long ngp_launch_count(void) { return __atomic_load_n(&g_ngp_launch_count, __ATOMIC_RELAXED); }
+
 // -------------------------------------------------------------------------------------------------
 // host: level table (tiny-cuda-nn GridEncoding constructor semantics)
 // -------------------------------------------------------------------------------------------------
@@ -78,25 +81,28 @@ extern "C" int ngp_cast_params(const float* src, uint16_t* dst_half, int64_t n, 
 #define NGP_SCHED_EAGER 1024  // rotated by eager launches (a collision needs two launches 1024 apart to overlap in time)
 #define NGP_SCHED_GRAPH 1024  // handed out once each to launches recorded into CUDA graphs (their slot is baked in)
 __device__ int g_sched[NGP_SCHED_EAGER + NGP_SCHED_GRAPH][2];
-// nullptr => the kernel falls back to static striding (graph slots exhausted)
+// nullptr => the kernel falls back to static striding (no current device / not queryable)
 static int* sched_slot(cudaStream_t st) {
     static int* bases[64] = {nullptr};  // per device: a __device__ symbol has one address per device
-    static unsigned eager_seq = 0, graph_seq = 0;
+    static unsigned eager_seq[64] = {0}, graph_seq[64] = {0};  // per device too (slots live in per-device memory)
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    if (!bases[dev]) {
+    int* base = __atomic_load_n(&bases[dev], __ATOMIC_ACQUIRE);
+    if (!base) {
         void* p = nullptr;
         if (cudaGetSymbolAddress(&p, g_sched) != cudaSuccess) return nullptr;
-        bases[dev] = (int*)p;
+        base = (int*)p;
+        __atomic_store_n(&bases[dev], base, __ATOMIC_RELEASE);  // every thread computes the same address
     }
-    int* base = bases[dev];
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) return nullptr;
     if (cs != cudaStreamCaptureStatusNone) {
-        if (graph_seq >= NGP_SCHED_GRAPH) return nullptr;
-        return base + 2 * (size_t)(NGP_SCHED_EAGER + graph_seq++);
+        // a captured launch keeps its slot for the life of the graph; when the pool is used up the slots are handed out
+        // again round-robin (two graphs then share one only if 1,024 captures lie between them AND they overlap in time)
+        const unsigned k = __atomic_fetch_add(&graph_seq[dev], 1u, __ATOMIC_RELAXED);
+        return base + 2 * (size_t)(NGP_SCHED_EAGER + k % NGP_SCHED_GRAPH);
     }
-    return base + 2 * (size_t)(eager_seq++ % NGP_SCHED_EAGER);
+    return base + 2 * (size_t)(__atomic_fetch_add(&eager_seq[dev], 1u, __ATOMIC_RELAXED) % NGP_SCHED_EAGER);
 }
 __device__ __forceinline__ void sched_finish(int* sched) {
     if (!sched) return;
@@ -1071,11 +1077,16 @@ extern "C" int ngp_net_backward_mlp(const NgpNet* net, const NgpSamples* smp, co
     if (rc) return rc;
     if (!dL_dsigmas || !dL_drgbs || !grad_enc || !grad_rgb) return NGP_EINVAL;
     if (smp->n == 0) return 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-        NGP_CUDA(cudaFuncSetAttribute(k_ngp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
-        NGP_CUDA(cudaFuncSetAttribute(k_ngp_bwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Bwd2Smem)));
-        attr_set = true;
+    {
+        // the dynamic shared-memory opt-in is a per-DEVICE function attribute: one process may drive several GPUs
+        static unsigned char attr_set[64] = {0};
+        int dev = 0;
+        NGP_CUDA(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || !__atomic_load_n(&attr_set[dev], __ATOMIC_ACQUIRE)) {
+            NGP_CUDA(cudaFuncSetAttribute(k_ngp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
+            NGP_CUDA(cudaFuncSetAttribute(k_ngp_bwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Bwd2Smem)));
+            if (dev >= 0 && dev < 64) __atomic_store_n(&attr_set[dev], 1, __ATOMIC_RELEASE);
+        }
     }
     static int variant = -1;  // NGP_BWD_VARIANT=0 selects the 8-warp all-at-once kernel (also used when re-gathering)
     if (variant < 0) {

@@ -79,7 +79,8 @@ __global__ void k_train_composite_fw(const NgpTrainCfg cfg, const int* __restric
                                      const float* __restrict__ sigmas, const float* __restrict__ rgbs,
                                      const float* __restrict__ deltas, const float* __restrict__ ts,
                                      float* __restrict__ rgb, float* __restrict__ opacity, float* __restrict__ depth,
-                                     float* __restrict__ ws, int* __restrict__ counters) {
+                                     float* __restrict__ ws, int* __restrict__ counters, const float* __restrict__ bg_dev) {
+    const float bg[3] = {bg_dev ? bg_dev[0] : cfg.bg[0], bg_dev ? bg_dev[1] : cfg.bg[1], bg_dev ? bg_dev[2] : cfg.bg[2]};
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= cfg.n_rays) return;
@@ -100,9 +101,9 @@ __global__ void k_train_composite_fw(const NgpTrainCfg cfg, const int* __restric
         const float rest = 1.0f - o.opacity;  // rgb += bg * (1 - opacity), reference rendering.py:160-161
         opacity[w] = o.opacity;
         depth[w] = o.depth;
-        rgb[3 * w] = o.r + cfg.bg[0] * rest;
-        rgb[3 * w + 1] = o.g + cfg.bg[1] * rest;
-        rgb[3 * w + 2] = o.b + cfg.bg[2] * rest;
+        rgb[3 * w] = o.r + bg[0] * rest;
+        rgb[3 * w + 1] = o.g + bg[1] * rest;
+        rgb[3 * w + 2] = o.b + bg[2] * rest;
         if (o.total_samples) atomicAdd(&counters[1], o.total_samples);
     }
 }
@@ -189,6 +190,7 @@ extern "C" int ngp_render_train_march(const NgpTrainCfg* cfg, const NgpTrainBuff
     } else {
         size_t temp_bytes = b->scan_temp_bytes;
         NGP_CUDA(cub::DeviceScan::ExclusiveSum(b->scan_temp, temp_bytes, b->n_samples, b->offsets, n, st));
+        NGP_COUNT_LAUNCHES(2);  // cub: init + sweep kernels
     }
     k_train_compact<<<ngp_div_up((int64_t)n * 32, 256), 256, 0, st>>>(*cfg, b->stage_t, b->stage_dt, b->n_samples, b->offsets,
                                                                        b->ray_idx, b->ts, b->deltas, b->counters);
@@ -207,7 +209,7 @@ extern "C" int ngp_render_train_net(const NgpNet* net, const NgpTrainCfg* cfg, c
     if (rc) return rc;
     k_train_composite_fw<<<ngp_div_up((int64_t)n * 32, 128), 128, 0, st>>>(*cfg, b->n_samples, b->offsets, b->sigmas, b->rgbs,
                                                                             b->deltas, b->ts, b->rgb, b->opacity, b->depth,
-                                                                            b->ws, b->counters);
+                                                                            b->ws, b->counters, b->bg_dev);
     NGP_CHECK_LAUNCH();
     return 0;
 }
@@ -229,7 +231,8 @@ __global__ void k_train_composite_bw(const NgpTrainCfg cfg, const int* __restric
                                      const float* __restrict__ dL_drgb, const float* __restrict__ dL_dopacity,
                                      const float* __restrict__ dL_ddepth, const float* __restrict__ dL_dws,
                                      float* __restrict__ dsigmas, float* __restrict__ drgbs, float* __restrict__ amax,
-                                     int* __restrict__ live_idx, int* __restrict__ counters) {
+                                     int* __restrict__ live_idx, int* __restrict__ counters, const float* __restrict__ bg_dev) {
+    const float bg[3] = {bg_dev ? bg_dev[0] : cfg.bg[0], bg_dev ? bg_dev[1] : cfg.bg[1], bg_dev ? bg_dev[2] : cfg.bg[2]};
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= cfg.n_rays) return;
@@ -250,8 +253,8 @@ __global__ void k_train_composite_bw(const NgpTrainCfg cfg, const int* __restric
     // route its gradient into the opacity gradient
     const float O = opacity[w];
     const float rest = 1.0f - O;
-    const float3 C = make_float3(rgb[3 * w] - cfg.bg[0] * rest, rgb[3 * w + 1] - cfg.bg[1] * rest, rgb[3 * w + 2] - cfg.bg[2] * rest);
-    const float dO = dL_dopacity[w] - (dC.x * cfg.bg[0] + dC.y * cfg.bg[1] + dC.z * cfg.bg[2]);
+    const float3 C = make_float3(rgb[3 * w] - bg[0] * rest, rgb[3 * w + 1] - bg[1] * rest, rgb[3 * w + 2] - bg[2] * rest);
+    const float dO = dL_dopacity[w] - (dC.x * bg[0] + dC.y * bg[1] + dC.z * bg[2]);
     const float dD = dL_ddepth ? dL_ddepth[w] : 0.f;
     float m = 0.f;
     const int n_comp = composite_ray_warp_bwd(
@@ -279,13 +282,14 @@ __global__ void k_train_composite_bw(const NgpTrainCfg cfg, const int* __restric
     }
 }
 
-__global__ void k_train_grad_scale(float* __restrict__ scalars, int* __restrict__ counters) {
+__global__ void k_train_grad_scale(float* __restrict__ scalars, int* __restrict__ counters, const int fused_loss) {
     // the live list is complete: publish its length and re-arm the append counter, so that counters[4] is zero
     // whenever a compositing backward starts, whatever the caller's order of calls
     counters[5] = counters[4];
     counters[4] = 0;
     // fused compositing + loss kernel: publish its sums ([4],[5] -> [2],[3]) and this step's sample counts, re-arm
-    if (scalars[4] != 0.f || scalars[5] != 0.f) {
+    // (unconditionally: a step whose sums are exactly zero must not leave the previous step's numbers behind)
+    if (fused_loss) {
         scalars[2] = scalars[4];
         scalars[3] = scalars[5];
         scalars[4] = 0.f;
@@ -313,7 +317,9 @@ __global__ void k_train_composite_loss(const NgpTrainCfg cfg, const int* __restr
                                        const float* __restrict__ deltas, const float* __restrict__ ts,
                                        const float* __restrict__ rgb_gt, float* __restrict__ rgb, float* __restrict__ opacity,
                                        float* __restrict__ depth, float* __restrict__ dsigmas, float* __restrict__ drgbs,
-                                       float* __restrict__ scalars, int* __restrict__ live_idx, int* __restrict__ counters) {
+                                       float* __restrict__ scalars, int* __restrict__ live_idx, int* __restrict__ counters,
+                                       const float* __restrict__ bg_dev) {
+    const float bg[3] = {bg_dev ? bg_dev[0] : cfg.bg[0], bg_dev ? bg_dev[1] : cfg.bg[1], bg_dev ? bg_dev[2] : cfg.bg[2]};
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= cfg.n_rays) return;
@@ -330,7 +336,7 @@ __global__ void k_train_composite_loss(const NgpTrainCfg cfg, const int* __restr
         [&](int i) { return make_float3(__ldg(cl + 3 * i), __ldg(cl + 3 * i + 1), __ldg(cl + 3 * i + 2)); },
         [&](int, float) {});
     const float rest = 1.0f - o.opacity;  // rgb += bg * (1 - opacity), reference rendering.py:160-161
-    const float3 out = make_float3(o.r + cfg.bg[0] * rest, o.g + cfg.bg[1] * rest, o.b + cfg.bg[2] * rest);
+    const float3 out = make_float3(o.r + bg[0] * rest, o.g + bg[1] * rest, o.b + bg[2] * rest);
     // NeRFLoss (reference losses.py:47-60, lambda_distortion = 0) and its per-ray gradients
     const float inv_n = 1.0f / (float)cfg.n_rays;
     const float ex = out.x - rgb_gt[3 * w], ey = out.y - rgb_gt[3 * w + 1], ez = out.z - rgb_gt[3 * w + 2];
@@ -347,7 +353,7 @@ __global__ void k_train_composite_loss(const NgpTrainCfg cfg, const int* __restr
     }
     if (n == 0) return;
     // backward: the background term routes the colour gradient into the opacity gradient
-    const float dO = cfg.lambda_opacity * (-lg - 1.0f) * inv_n - (dC.x * cfg.bg[0] + dC.y * cfg.bg[1] + dC.z * cfg.bg[2]);
+    const float dO = cfg.lambda_opacity * (-lg - 1.0f) * inv_n - (dC.x * bg[0] + dC.y * bg[1] + dC.z * bg[2]);
     float* ds = dsigmas + start;
     float* dc = drgbs + 3 * start;
     float m = 0.f;
@@ -388,9 +394,9 @@ extern "C" int ngp_render_train_step(const NgpNet* net, const NgpTrainCfg* cfg, 
     if (rc) return rc;
     k_train_composite_loss<<<ngp_div_up((int64_t)n * 32, 128), 128, 0, st>>>(
         *cfg, b->n_samples, b->offsets, b->sigmas, b->rgbs, b->deltas, b->ts, rgb_gt, b->rgb, b->opacity, b->depth, b->dsigmas,
-        b->drgbs, b->scalars, b->live_idx, b->counters);
+        b->drgbs, b->scalars, b->live_idx, b->counters, b->bg_dev);
     NGP_CHECK_LAUNCH();
-    k_train_grad_scale<<<1, 1, 0, st>>>(b->scalars, b->counters);
+    k_train_grad_scale<<<1, 1, 0, st>>>(b->scalars, b->counters, 1);
     NGP_CHECK_LAUNCH();
     if (b->live_idx) {
         smp.live_idx = b->live_idx;
@@ -411,9 +417,9 @@ extern "C" int ngp_render_train_bwd(const NgpNet* net, const NgpTrainCfg* cfg, c
     const int n = cfg->n_rays;
     k_train_composite_bw<<<ngp_div_up((int64_t)n * 32, 128), 128, 0, st>>>(
         *cfg, b->n_samples, b->offsets, b->sigmas, b->rgbs, b->deltas, b->ts, b->ws, b->rgb, b->opacity, b->depth, dL_drgb,
-        dL_dopacity, dL_ddepth, dL_dws, b->dsigmas, b->drgbs, b->scalars, b->live_idx, b->counters);
+        dL_dopacity, dL_ddepth, dL_dws, b->dsigmas, b->drgbs, b->scalars, b->live_idx, b->counters, b->bg_dev);
     NGP_CHECK_LAUNCH();
-    k_train_grad_scale<<<1, 1, 0, st>>>(b->scalars, b->counters);
+    k_train_grad_scale<<<1, 1, 0, st>>>(b->scalars, b->counters, 0);
     NGP_CHECK_LAUNCH();
     NgpSamples smp = train_samples(cfg, b);
     if (b->live_idx && b->feat_save) {
@@ -536,89 +542,6 @@ __global__ void k_adam(float* __restrict__ p, float* __restrict__ g, float* __re
         if (ph) ph[i] = __float2half_rn(p[i]);
     }
 }
-// (Experiment, NGP_ADAM_VARIANT=1; slower than k_adam inside the pipelined step, see ngp_adam_step.)
-// The same update with the stream staged through SHARED memory: every thread keeps ADAM_STAGES-1 tiles of (param, grad, m,
-// v) in flight as 16-byte cp.async copies into its own shared-memory slots (no barrier: a thread consumes only what it
-// copied itself). The ~12 MB that must be in flight to saturate HBM then live in shared memory, not in registers, so the
-// kernel needs one 256-thread CTA per SM and ~10 K registers of it -- the next step's march, which the trainer runs under
-// this kernel on another stream and which needs registers but no shared memory, keeps almost its full occupancy.
-#define ADAM_THREADS 256
-#define ADAM_STAGES 6
-__device__ __forceinline__ void cp_async16_hint(void* smem_dst, const void* gmem_src, uint64_t policy) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "l"(policy) : "memory");
-}
-__global__ void __launch_bounds__(ADAM_THREADS, 1)
-k_adam_staged(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-              __half* __restrict__ ph, int64_t n, const float* __restrict__ lr_dev, const int* __restrict__ step_dev, float beta1,
-              float beta2, float eps, float grad_mul) {
-    extern __shared__ __align__(16) float4 adam_buf[];  // [stage][array 0..3][thread]
-    const int t = *step_dev + 1;
-    const float lr = *lr_dev;
-    const float bc1 = 1.0f - powf(beta1, (float)t);
-    const float bc2 = 1.0f - powf(beta2, (float)t);
-    const float step_size = lr / bc1;
-    const float inv_sqrt_bc2 = rsqrtf(bc2);
-    const int64_t n4 = n >> 2;
-    const int64_t n_tiles = (n4 + ADAM_THREADS - 1) / ADAM_THREADS;
-    const uint64_t stream_pol = l2_policy_evict_first(), keep_pol = l2_policy_evict_last();
-    const int tid = threadIdx.x;
-    auto slot = [&](int stage, int arr) { return adam_buf + ((size_t)stage * 4 + arr) * ADAM_THREADS + tid; };
-    auto issue = [&](int64_t tile, int stage) {
-        const int64_t i = tile * ADAM_THREADS + tid;
-        if (tile < n_tiles && i < n4) {
-            cp_async16_hint(slot(stage, 0), reinterpret_cast<const float4*>(p) + i, stream_pol);
-            cp_async16_hint(slot(stage, 1), reinterpret_cast<const float4*>(g) + i, stream_pol);
-            cp_async16_hint(slot(stage, 2), reinterpret_cast<const float4*>(m) + i, stream_pol);
-            cp_async16_hint(slot(stage, 3), reinterpret_cast<const float4*>(v) + i, stream_pol);
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");  // one group per tile, empty or not
-    };
-#pragma unroll
-    for (int s = 0; s < ADAM_STAGES - 1; ++s) issue((int64_t)blockIdx.x + (int64_t)s * gridDim.x, s);
-    int stage = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        issue(tile + (int64_t)(ADAM_STAGES - 1) * gridDim.x, (stage + ADAM_STAGES - 1) % ADAM_STAGES);
-        asm volatile("cp.async.wait_group %0;" ::"n"(ADAM_STAGES - 1) : "memory");  // this tile's group has landed
-        const int64_t i = tile * ADAM_THREADS + tid;
-        if (i < n4) {
-            float4 pv = *slot(stage, 0), gv = *slot(stage, 1), mv = *slot(stage, 2), vv = *slot(stage, 3);
-            float* pp = &pv.x; float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float gr = gp[k] * grad_mul;
-                mp[k] = beta1 * mp[k] + (1.0f - beta1) * gr;
-                vp[k] = beta2 * vp[k] + (1.0f - beta2) * gr * gr;
-                const float denom = sqrtf(vp[k]) * inv_sqrt_bc2 + eps;
-                pp[k] -= step_size * (mp[k] / denom);
-            }
-            st_f4_hint(reinterpret_cast<float4*>(p) + i, pv, stream_pol);
-            st_f4_hint(reinterpret_cast<float4*>(m) + i, mv, stream_pol);
-            st_f4_hint(reinterpret_cast<float4*>(v) + i, vv, stream_pol);
-            reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ph) {
-                uint2 h;
-                h.x = pack_half2(pv.x, pv.y);
-                h.y = pack_half2(pv.z, pv.w);
-                st_u2_hint(reinterpret_cast<uint2*>(ph) + i, h, keep_pol);
-            }
-        }
-        stage = (stage + 1) % ADAM_STAGES;
-    }
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    // tail (n % 4 elements)
-    if (blockIdx.x == 0) {
-        for (int64_t i = (n4 << 2) + tid; i < n; i += ADAM_THREADS) {
-            const float gr = g[i] * grad_mul;
-            m[i] = beta1 * m[i] + (1.0f - beta1) * gr;
-            v[i] = beta2 * v[i] + (1.0f - beta2) * gr * gr;
-            p[i] -= step_size * (m[i] / (sqrtf(v[i]) * inv_sqrt_bc2 + eps));
-            g[i] = 0.f;
-            if (ph) ph[i] = __float2half_rn(p[i]);
-        }
-    }
-}
-
 __global__ void k_step_inc(int* step) { *step += 1; }
 
 extern "C" int ngp_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, uint16_t* params_half, int64_t n,
@@ -629,33 +552,15 @@ extern "C" int ngp_adam_step(float* params, float* grads, float* exp_avg, float*
         return NGP_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     if (n > 0) {
-        // NGP_ADAM_VARIANT (env, read once): 0 = register stream (default), 1 = shared-memory staged stream. Measured inside the
-        // pipelined step on B200: 0.378 ms/step with 0 (2 blocks/SM; 3 -> 0.394, 4 -> 0.390, 1 -> 0.411) vs 0.393 with 1.
-        static int variant = -1;
-        if (variant < 0) {
-            const char* e = getenv("NGP_ADAM_VARIANT");
-            variant = e ? atoi(e) : 0;
-        }
-        if (variant == 1) {
-            const size_t smem = (size_t)ADAM_STAGES * 4 * ADAM_THREADS * sizeof(float4);
-            static bool attr_set = false;
-            if (!attr_set) {
-                NGP_CUDA(cudaFuncSetAttribute(k_adam_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                attr_set = true;
-            }
-            int grid = ngp_div_up((n >> 2) + 1, ADAM_THREADS);
-            if (grid > ngp_sm_count()) grid = ngp_sm_count();
-            k_adam_staged<<<grid, ADAM_THREADS, smem, st>>>(params, grads, exp_avg, exp_avg_sq, (__half*)params_half, n, lr_dev,
-                                                            step_dev, beta1, beta2, eps, grad_mul);
-        } else {
-            // 2 resident blocks per SM (two 64-byte groups per thread in flight) saturate HBM and leave registers for the
-            // next step's march, which a trainer overlaps with this kernel on another stream
-            int grid = ngp_div_up((n >> 2) + 1, 256);
-            const int cap = ngp_sm_count() * 2;
-            if (grid > cap) grid = cap;
-            k_adam<<<grid, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, (__half*)params_half, n, lr_dev, step_dev, beta1,
-                                          beta2, eps, grad_mul);
-        }
+        // 2 resident blocks per SM (two 64-byte groups per thread in flight) saturate HBM and leave registers for the
+        // next step's march, which a trainer overlaps with this kernel on another stream (measured inside the pipelined
+        // step on B200: 0.378 ms/step with 2 blocks/SM; 3 -> 0.394, 4 -> 0.390, 1 -> 0.411; a shared-memory staged
+        // cp.async variant: 0.393)
+        int grid = ngp_div_up((n >> 2) + 1, 256);
+        const int cap = ngp_sm_count() * 2;
+        if (grid > cap) grid = cap;
+        k_adam<<<grid, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, (__half*)params_half, n, lr_dev, step_dev, beta1,
+                                      beta2, eps, grad_mul);
         NGP_CHECK_LAUNCH();
     }
     if (increment_step) {
@@ -750,6 +655,213 @@ extern "C" int ngp_adam_step_p2p(int world, int rank, const uint64_t* peer_grads
                                           eps, 1.0f / (float)world);
         NGP_CHECK_LAUNCH();
     }
+    if (increment_step) {
+        k_step_inc<<<1, 1, 0, st>>>(step_dev);
+        NGP_CHECK_LAUNCH();
+    }
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// The same exchange as ONE self-synchronising kernel (no host-side barriers, CUDA-graph capturable):
+//   start barrier : block 0 tells every peer "my gradients are complete" (flag store, release.sys) and waits for
+//                   the same word from every peer, then releases the other blocks through a local flag;
+//   body          : reduce-scatter (peer loads, or ONE multimem.ld_reduce per 16 bytes when the buffers have an
+//                   NVLS multicast mapping: the switch sums the N copies, 1/N of the inbound NVLink bytes)
+//                   -> Adam on the owned shard -> all-gather of the new fp16 parameters (peer stores, or ONE
+//                   multimem.st); every block also clears its slice of `zero_buf`, the gradient buffer the NEXT
+//                   step accumulates into (gradient buffers alternate, so nobody clears a buffer a peer may still read);
+//   end barrier   : the last block to finish fences, tells every peer "my parameter stores are done", waits for the
+//                   same from every peer and bumps the epoch. The kernel therefore ends only when this rank's fp16
+//                   working copy is complete and every peer is done reading this rank's gradients.
+// Flags are monotonically increasing epochs (never reset), so replays need no re-arming. A rank that waits more
+// than ~4 s (a peer died) sets sync[2] = 1 and carries on; the host checks it (ngp_fused_sync_error).
+// -------------------------------------------------------------------------------------------------
+struct FusedPeers {
+    const float* grads[NGP_MAX_PEERS];
+    __half* params_half[NGP_MAX_PEERS];
+    uint32_t* flags[NGP_MAX_PEERS];  // per rank: [0,world) arrive slots, [NGP_MAX_PEERS, NGP_MAX_PEERS+world) done slots
+    const float* mc_grads;           // multicast (NVLS) alias of the gradient buffer, or nullptr
+    __half* mc_params_half;          // multicast alias of the fp16 working copy, or nullptr
+};
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// spin until *p has reached epoch e (wrap-safe); false on timeout
+template <bool SYS>
+__device__ __forceinline__ bool wait_epoch(const uint32_t* p, uint32_t e) {
+    const long long t0 = clock64();
+    for (;;) {
+        const uint32_t v = SYS ? ld_acquire_sys(p) : ld_acquire_gpu(p);
+        if ((int32_t)(v - e) >= 0) return true;
+        if (clock64() - t0 > 8000000000ll) return false;
+        __nanosleep(64);
+    }
+}
+__device__ __forceinline__ float4 multimem_ld_reduce_f4(const float* mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(mc)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ void multimem_st_u2(void* mc, uint2 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1,%2};" ::"l"(mc), "f"(__uint_as_float(v.x)),
+                 "f"(__uint_as_float(v.y))
+                 : "memory");
+}
+
+// sync (local device memory, uint32): [0] epoch of the last completed call, [1] finished-block counter, [2] error flag,
+// [3] go flag (start barrier passed, written by block 0)
+template <int W>  // W >= world: bounds the peer-load registers (16 float4 in flight per thread would halve the occupancy)
+__global__ void __launch_bounds__(256, 3)
+k_adam_fused(const FusedPeers peers, const int world, const int rank, float* __restrict__ p, float* __restrict__ m,
+             float* __restrict__ v, const int64_t lo4, const int64_t hi4, float4* __restrict__ zero_buf, const int64_t zero_n4,
+             uint32_t* __restrict__ sync, const float* __restrict__ lr_dev, const int* __restrict__ step_dev, float beta1,
+             float beta2, float eps, float grad_mul) {
+    __shared__ uint32_t s_e;
+    // ---- start barrier ----
+    if (threadIdx.x == 0) s_e = sync[0] + 1u;  // sync[0] is only written by the last block of the previous call
+    __syncthreads();
+    const uint32_t e = s_e;
+    if (blockIdx.x == 0) {
+        if ((int)threadIdx.x < world) {
+            st_release_sys(peers.flags[threadIdx.x] + rank, e);
+            if (!wait_epoch<true>(peers.flags[rank] + threadIdx.x, e)) sync[2] = 1u;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) st_release_gpu(&sync[3], e);
+    } else {
+        if (threadIdx.x == 0 && !wait_epoch<false>(&sync[3], e)) sync[2] = 1u;
+        __syncthreads();
+    }
+    // the clear of the next step's gradient buffer is local and independent: issue it first so the writes drain
+    // while the peer loads are in flight
+    {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < zero_n4; i += (int64_t)gridDim.x * blockDim.x)
+            zero_buf[i] = z;
+    }
+    const int t = *step_dev + 1;
+    const float lr = *lr_dev;
+    const float bc1 = 1.0f - powf(beta1, (float)t);
+    const float bc2 = 1.0f - powf(beta2, (float)t);
+    const float step_size = lr / bc1;
+    const float inv_sqrt_bc2 = rsqrtf(bc2);
+    const uint64_t stream_pol = l2_policy_evict_first();
+    const bool mc_in = peers.mc_grads != nullptr, mc_out = peers.mc_params_half != nullptr;
+    for (int64_t i = lo4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < hi4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 g;
+        if (mc_in) {
+            g = multimem_ld_reduce_f4(peers.mc_grads + 4 * i);
+        } else {
+            g = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 part[W];
+#pragma unroll
+            for (int r = 0; r < W; ++r)
+                if (r < world) part[r] = __ldcg(reinterpret_cast<const float4*>(peers.grads[r]) + i);  // all loads in flight
+#pragma unroll
+            for (int r = 0; r < W; ++r)
+                if (r < world) { g.x += part[r].x; g.y += part[r].y; g.z += part[r].z; g.w += part[r].w; }
+        }
+        float4 pv = ld_f4_hint(reinterpret_cast<const float4*>(p) + i, stream_pol);
+        float4 mv = ld_f4_hint(reinterpret_cast<const float4*>(m) + i, stream_pol);
+        float4 vv = ld_f4_hint(reinterpret_cast<const float4*>(v) + i, stream_pol);
+        float* pp = &pv.x; float* gp = &g.x; float* mp = &mv.x; float* vp = &vv.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gr = gp[k] * grad_mul;
+            mp[k] = beta1 * mp[k] + (1.0f - beta1) * gr;
+            vp[k] = beta2 * vp[k] + (1.0f - beta2) * gr * gr;
+            pp[k] -= step_size * (mp[k] / (sqrtf(vp[k]) * inv_sqrt_bc2 + eps));
+        }
+        st_f4_hint(reinterpret_cast<float4*>(p) + i, pv, stream_pol);
+        st_f4_hint(reinterpret_cast<float4*>(m) + i, mv, stream_pol);
+        st_f4_hint(reinterpret_cast<float4*>(v) + i, vv, stream_pol);
+        uint2 h;
+        h.x = pack_half2(pv.x, pv.y);
+        h.y = pack_half2(pv.z, pv.w);
+        if (mc_out) {
+            multimem_st_u2(reinterpret_cast<uint2*>(peers.mc_params_half) + i, h);
+        } else {
+#pragma unroll
+            for (int r = 0; r < W; ++r)
+                if (r < world) reinterpret_cast<uint2*>(peers.params_half[r])[i] = h;
+        }
+    }
+    // ---- end barrier: last block to finish ----
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(&sync[1], 1u) == gridDim.x - 1u) {
+            __threadfence_system();
+            sync[1] = 0u;
+            for (int r = 0; r < world; ++r) st_release_sys(peers.flags[r] + NGP_MAX_PEERS + rank, e);
+            for (int r = 0; r < world; ++r)
+                if (!wait_epoch<true>(peers.flags[rank] + NGP_MAX_PEERS + r, e)) sync[2] = 1u;
+            sync[0] = e;
+            __threadfence();
+        }
+    }
+}
+
+extern "C" int ngp_adam_step_fused(int world, int rank, const uint64_t* peer_grads, const uint64_t* peer_params_half,
+                                   const uint64_t* peer_flags, uint64_t mc_grads, uint64_t mc_params_half, float* params,
+                                   float* exp_avg, float* exp_avg_sq, int64_t n, float* zero_buf, uint32_t* sync,
+                                   const float* lr_dev, int32_t* step_dev, float beta1, float beta2, float eps,
+                                   int increment_step, void* stream) {
+    if (world < 1 || world > NGP_MAX_PEERS || rank < 0 || rank >= world || !peer_grads || !peer_params_half || !peer_flags ||
+        !params || !exp_avg || !exp_avg_sq || !sync || !lr_dev || !step_dev || n < 0 || (n & 3))
+        return NGP_EINVAL;
+    FusedPeers pp;
+    for (int r = 0; r < NGP_MAX_PEERS; ++r) {
+        pp.grads[r] = r < world ? (const float*)(uintptr_t)peer_grads[r] : nullptr;
+        pp.params_half[r] = r < world ? (__half*)(uintptr_t)peer_params_half[r] : nullptr;
+        pp.flags[r] = r < world ? (uint32_t*)(uintptr_t)peer_flags[r] : nullptr;
+        if (r < world && (((uintptr_t)pp.grads[r] & 15) || ((uintptr_t)pp.params_half[r] & 7) || ((uintptr_t)pp.flags[r] & 3) ||
+                          !pp.flags[r]))
+            return NGP_EINVAL;
+    }
+    pp.mc_grads = (const float*)(uintptr_t)mc_grads;
+    pp.mc_params_half = (__half*)(uintptr_t)mc_params_half;
+    if ((mc_grads & 15) || (mc_params_half & 7)) return NGP_EINVAL;
+    if (((uintptr_t)params | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq | (uintptr_t)zero_buf) & 15) return NGP_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n4 = n >> 2;
+    const int64_t base = n4 / world, extra = n4 % world;
+    const int64_t lo4 = rank * base + (rank < extra ? rank : extra);
+    const int64_t hi4 = lo4 + base + (rank < extra ? 1 : 0);
+    // every block passes both barriers, so the grid must not exceed what is guaranteed to become resident while others
+    // spin: blocks only wait on block 0 (the first one dispatched) and on peers, never on later blocks of this grid
+    int64_t work = hi4 - lo4;
+    if (zero_buf && n4 > work) work = n4;
+    int grid = ngp_div_up(work > 0 ? work : 1, 256 * 4);
+    const int cap = ngp_sm_count() * 3;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+#define NGP_LAUNCH_FUSED(W)                                                                                                \
+    k_adam_fused<W><<<grid, 256, 0, st>>>(pp, world, rank, params, exp_avg, exp_avg_sq, lo4, hi4, (float4*)zero_buf,       \
+                                          zero_buf ? n4 : 0, sync, lr_dev, step_dev, beta1, beta2, eps, 1.0f / (float)world)
+    if (world <= 2) NGP_LAUNCH_FUSED(2);
+    else if (world <= 4) NGP_LAUNCH_FUSED(4);
+    else if (world <= 8) NGP_LAUNCH_FUSED(8);
+    else NGP_LAUNCH_FUSED(16);
+#undef NGP_LAUNCH_FUSED
+    NGP_CHECK_LAUNCH();
     if (increment_step) {
         k_step_inc<<<1, 1, 0, st>>>(step_dev);
         NGP_CHECK_LAUNCH();
@@ -930,12 +1042,16 @@ __global__ void k_grid_scatter(const int* __restrict__ cell_idx, const float* __
 }
 
 // grid = grid < 0 ? grid : max(grid*decay, tmp); accumulate sum / count of the positive cells
+// erode (count_grid != NULL, reference networks.py:258-260): cells seen by few cameras decay faster,
+// decay_i = clamp(decay^(1/count_i), 0.1, 0.95)
 __global__ void k_grid_merge(float* __restrict__ grid, const float* __restrict__ tmp, int64_t n, float decay,
-                             float* __restrict__ stats /* [0]=sum, [1]=count */) {
+                             const float* __restrict__ count_grid, float* __restrict__ stats /* [0]=sum, [1]=count */) {
     float s = 0.f, cnt = 0.f;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float g = grid[i];
-        if (!(g < 0.f)) g = fmaxf(g * decay, tmp[i]);
+        float d = decay;
+        if (count_grid) d = fminf(fmaxf(powf(decay, 1.0f / count_grid[i]), 0.1f), 0.95f);
+        if (!(g < 0.f)) g = fmaxf(g * d, tmp[i]);
         grid[i] = g;
         if (g > 0.f) { s += g; cnt += 1.f; }
     }
@@ -968,9 +1084,10 @@ extern "C" size_t ngp_update_grid_workspace(int cascades, int grid_size) {
            select_temp_bytes((int)g3);
 }
 
-extern "C" int ngp_update_density_grid(const NgpNet* net, float* density_grid, uint8_t* density_bitfield, int cascades,
-                                       int grid_size, float scale, float density_threshold, int warmup, float decay,
-                                       uint32_t seed, void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int ngp_update_density_grid(const NgpNet* net, float* density_grid, uint8_t* density_bitfield,
+                                       const float* count_grid, int cascades, int grid_size, float scale,
+                                       float density_threshold, int warmup, float decay, uint32_t seed, void* workspace,
+                                       size_t workspace_bytes, void* stream) {
     if (!net || !density_grid || !density_bitfield || !workspace || cascades < 1 || grid_size < 2 || grid_size > 1024)
         return NGP_EINVAL;
     if (workspace_bytes < ngp_update_grid_workspace(cascades, grid_size)) return NGP_EINVAL;
@@ -993,6 +1110,7 @@ extern "C" int ngp_update_density_grid(const NgpNet* net, float* density_grid, u
     u.g3 = (uint32_t)g3; u.M = (uint32_t)(g3 / 4); u.scale = scale; u.seed = seed;
     NGP_CUDA(cudaMemsetAsync(tmp, 0, cascades * g3 * 4, st));
     NGP_CUDA(cudaMemsetAsync(stats, 0, 16, st));
+    NGP_COUNT_LAUNCHES(2);
     const uint32_t n_slots = warmup ? (uint32_t)g3 : 2u * u.M;
     for (int c = 0; c < cascades; ++c) {
         if (!warmup) {
@@ -1000,6 +1118,7 @@ extern "C" int ngp_update_density_grid(const NgpNet* net, float* density_grid, u
             NGP_CHECK_LAUNCH();
             NGP_CUDA(cub::DeviceSelect::Flagged(cub_temp, cub_bytes, cub::CountingInputIterator<int>(0), flags, occ_list,
                                                 occ_count, (int)g3, st));
+            NGP_COUNT_LAUNCHES(2);  // cub: init + sweep kernels
         }
         k_grid_pick<<<ngp_div_up(n_slots, 256), 256, 0, st>>>(u, c, occ_list, occ_count, cell_idx, xyz);
         NGP_CHECK_LAUNCH();
@@ -1013,7 +1132,7 @@ extern "C" int ngp_update_density_grid(const NgpNet* net, float* density_grid, u
     }
     int grid = ngp_div_up((int64_t)cascades * g3, 256);
     if (grid > ngp_sm_count() * 8) grid = ngp_sm_count() * 8;
-    k_grid_merge<<<grid, 256, 0, st>>>(density_grid, tmp, (int64_t)cascades * g3, decay, stats);
+    k_grid_merge<<<grid, 256, 0, st>>>(density_grid, tmp, (int64_t)cascades * g3, decay, count_grid, stats);
     NGP_CHECK_LAUNCH();
     k_grid_mean<<<1, 1, 0, st>>>(stats);
     NGP_CHECK_LAUNCH();

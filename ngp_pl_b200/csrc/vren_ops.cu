@@ -387,6 +387,7 @@ extern "C" int ngp_raymarching_train(const float* rays_o, const float* rays_d, c
 #undef NGP_LAUNCH_STAGE
         NGP_CHECK_LAUNCH();
         NGP_CUDA(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, n_samples, offsets, n_rays, st));
+        NGP_COUNT_LAUNCHES(2);  // cub: init + sweep kernels
         k_march_train_expand<<<mg, 128, 0, st>>>(rays_o, rays_d, stage, max_samples, n_rays, n_samples, offsets, rays_a, xyzs,
                                                  dirs, deltas, ts, counter);
         NGP_CHECK_LAUNCH();
@@ -398,6 +399,7 @@ extern "C" int ngp_raymarching_train(const float* rays_o, const float* rays_d, c
                                                                 n_samples);
     NGP_CHECK_LAUNCH();
     NGP_CUDA(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, n_samples, offsets, n_rays, st));
+    NGP_COUNT_LAUNCHES(2);  // cub: init + sweep kernels
     k_march_train_write<<<ngp_div_up(n_rays, bs), bs, 0, st>>>(rays_o, rays_d, hits_t, noise, density_bitfield, cascades,
                                                                 grid_size, scale, exp_step_factor, max_samples, n_rays,
                                                                 n_samples, offsets, rays_a, xyzs, dirs, deltas, ts, counter);

@@ -132,6 +132,10 @@ def camera_poses(n, radius=1.5, seed=0, upper_only=True):
     return poses
 
 
+def camera_radius(scene):
+    return 1.5 if scene.scale <= 0.5 else 2.5
+
+
 def get_rays(directions, c2w):
     """directions (N,3), c2w (3,4) or (N,3,4) -> rays_o, rays_d (reference datasets/ray_utils.py:46-70)."""
     if c2w.dim() == 2:
@@ -171,12 +175,16 @@ class RayBank:
     """Training images of a synthetic scene as flat device tensors + the reference's per-step random
     sampling of (image, pixel) pairs with replacement (reference datasets/base.py:22-30)."""
 
-    def __init__(self, scene, n_images=100, K=None, device="cuda", seed=0, store_dtype=torch.uint8):
+    def __init__(self, scene, n_images=100, K=None, device="cuda", seed=0, store_dtype=torch.uint8, radius=None):
         self.scene = scene
         self.K = K or intrinsics()
         self.device = device
         self.directions = ray_directions(self.K, device)
-        self.poses = torch.as_tensor(camera_poses(n_images, seed=seed), device=device)
+        # bounded scenes: cameras on the radius-1.5 upper hemisphere (Synthetic-NeRF); unbounded (scale > 0.5): inside the
+        # far shell, all around the central content
+        radius = camera_radius(scene) if radius is None else radius
+        self.poses = torch.as_tensor(camera_poses(n_images, radius=radius, seed=seed, upper_only=scene.scale <= 0.5),
+                                     device=device)
         n_pix = self.directions.shape[0]
         self.rgb = torch.empty(n_images, n_pix, 3, device=device, dtype=store_dtype)
         for i in range(n_images):

@@ -75,14 +75,36 @@ def shard_range(n_items, world_size, rank):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-_SET_FIELDS = ("rays_o", "rays_d", "rgb_gt", "noise", "n_samples", "offsets", "counters", "ray_idx", "ts", "deltas")
+class CosineAnnealingLR:
+    """The reference's learning-rate schedule (train.py:135-137): torch.optim.lr_scheduler.CosineAnnealingLR(opt,
+    T_max=num_epochs, eta_min=lr/30), which pytorch-lightning steps once per EPOCH; a training epoch of the reference is
+    1000 optimiser steps (datasets/base.py:17-19). So the rate is piecewise constant:
+        lr(step) = eta_min + (lr0 - eta_min) * (1 + cos(pi * epoch / T_max)) / 2,   epoch = step // steps_per_epoch.
+    Trainer(lr_schedule=...) writes it into the device-resident `lr` the Adam kernels read (stream-ordered fill, no sync,
+    no graph re-capture)."""
+
+    def __init__(self, base_lr, T_max=30, eta_min=None, steps_per_epoch=1000):
+        self.base_lr = float(base_lr)
+        self.T_max = int(T_max)
+        self.eta_min = float(base_lr) / 30 if eta_min is None else float(eta_min)
+        self.steps_per_epoch = int(steps_per_epoch)
+
+    def lr_at_epoch(self, epoch):
+        return self.eta_min + (self.base_lr - self.eta_min) * (1 + math.cos(math.pi * epoch / self.T_max)) / 2
+
+    def lr_at_step(self, step):
+        return self.lr_at_epoch(step // self.steps_per_epoch)
+
+
+_SET_FIELDS = ("rays_o", "rays_d", "rgb_gt", "noise", "n_samples", "offsets", "counters", "ray_idx", "ts", "deltas", "bg")
 
 
 class Trainer:
     def __init__(self, model: NGP, n_rays=8192, lr=1e-2, exp_step_factor=0.0, bg=(1.0, 1.0, 1.0), lambda_opacity=1e-3,
                  T_threshold=1e-4, betas=(0.9, 0.999), eps=1e-15, max_total_samples=None, update_interval=16,
                  warmup_steps=256, process_group=None, world_size=1, rank=0, seed=0, materialize_ws=False, ddp="nccl",
-                 lambda_distortion=0.0, skip_dead_samples=True, fused_loss=True):
+                 lambda_distortion=0.0, skip_dead_samples=True, fused_loss=True, random_bg=False, erode=False,
+                 lr_schedule=None):
         self.model = model
         dev = model.density_bitfield.device
         if dev.type != "cuda":
@@ -105,8 +127,18 @@ class Trainer:
         # "zero": NCCL reduce_scatter of the gradient + Adam on this rank's 1/N shard + all_gather of the fp16 working
         #         copy: 3/4 of all_reduce's traffic ((N-1)/N * (4+2) instead of 2*(N-1)/N * 4 bytes per parameter) and 1/N of
         #         the optimiser's HBM traffic;
-        # "p2p" : the same algorithm as ONE kernel over NVLink peer memory (ngp_adam_step_p2p)
+        # "p2p" : the same algorithm as ONE self-synchronising kernel over NVLink peer memory (ngp_adam_step_fused: flag
+        #         barriers inside the kernel, captured into the step's CUDA graph, gradient buffers alternate so the clear
+        #         of the next one rides in the same kernel);
+        # "nvls": "p2p" with the NVSwitch doing the sum / the replication (multimem.ld_reduce / multimem.st on the
+        #         multicast mapping of the symmetric buffers);
+        # "p2p_host": round 1's variant of "p2p" (host-launched barriers around ngp_adam_step_p2p), kept for comparison
         self.ddp = ddp if self.world_size > 1 else "none"
+        self.random_bg = bool(random_bg)   # reference rendering.py:153-161 (one random colour per training batch)
+        self.erode = bool(erode)           # reference networks.py:258-260 / train.py:163 (needs model.count_grid)
+        self.lr_schedule = lr_schedule     # e.g. CosineAnnealingLR(lr, T_max=30, steps_per_epoch=1000)
+        self._n_gbuf = 2 if self.ddp in ("p2p", "nvls") else 1
+        self._gcur = 0
         L = _lib.lib()
 
         # ---- flat parameter / gradient / optimiser state --------------------------------------------------
@@ -120,28 +152,47 @@ class Trainer:
             self.P[self.n_enc:].copy_(pr.data)
             pe.data = self.P[:self.n_enc]
             pr.data = self.P[self.n_enc:]
-            if self.ddp == "p2p":
-                # gradient buffer and fp16 working copy live in symmetric (peer-mapped) memory
+            if self.ddp in ("p2p", "nvls", "p2p_host"):
+                # gradient buffer(s), fp16 working copy and the barrier flags live in symmetric (peer-mapped) memory
                 import torch.distributed as dist
                 import torch.distributed._symmetric_memory as symm_mem
+                if n % 4:
+                    raise RuntimeError("the fused exchange needs a parameter count that is a multiple of 4")
                 grp = self.pg if self.pg is not None else dist.group.WORLD
-                self.G = symm_mem.empty(n, dtype=torch.float32, device=dev)
-                self.G.zero_()
+                W = self.world_size
+                self._G2 = symm_mem.empty(self._n_gbuf * n, dtype=torch.float32, device=dev)
+                self._G2.zero_()
+                self._Gs = [self._G2[b * n:(b + 1) * n] for b in range(self._n_gbuf)]
                 self.Ph = symm_mem.empty(n, dtype=torch.float16, device=dev)
-                self.hG = symm_mem.rendezvous(self.G, grp)
+                self._flags = symm_mem.empty(64, dtype=torch.int32, device=dev)
+                self._flags.zero_()
+                self._sync = torch.zeros(8, device=dev, dtype=torch.int32)
+                self.hG = symm_mem.rendezvous(self._G2, grp)
                 self.hPh = symm_mem.rendezvous(self.Ph, grp)
-                self.peer_G = (C.c_uint64 * self.world_size)(*[int(p) for p in self.hG.buffer_ptrs])
-                self.peer_Ph = (C.c_uint64 * self.world_size)(*[int(p) for p in self.hPh.buffer_ptrs])
+                self.hFl = symm_mem.rendezvous(self._flags, grp)
+                self.peer_Gs = [(C.c_uint64 * W)(*[int(p) + 4 * n * b for p in self.hG.buffer_ptrs]) for b in range(self._n_gbuf)]
+                self.peer_G = self.peer_Gs[0]
+                self.peer_Ph = (C.c_uint64 * W)(*[int(p) for p in self.hPh.buffer_ptrs])
+                self.peer_flags = (C.c_uint64 * W)(*[int(p) for p in self.hFl.buffer_ptrs])
+                self.mc_Gs, self.mc_Ph = [0] * self._n_gbuf, 0
+                if self.ddp == "nvls":
+                    mg, mp = int(getattr(self.hG, "multicast_ptr", 0) or 0), int(getattr(self.hPh, "multicast_ptr", 0) or 0)
+                    if not mg or not mp:
+                        raise RuntimeError("ddp='nvls': the symmetric allocations have no multicast (NVLS) mapping on this system")
+                    self.mc_Gs = [mg + 4 * n * b for b in range(self._n_gbuf)]
+                    self.mc_Ph = mp
+                torch.cuda.synchronize(dev)
+                dist.barrier(group=self.pg)  # every rank's flags / gradients are zero before anyone's first exchange
             elif self.ddp == "zero":
                 # equal shards for reduce_scatter / all_gather: pad the flat buffers to a multiple of 4 * world
                 lo, hi, n_pad = zero_shard(n, self.world_size, self.rank)
                 self._zero = (lo, hi, n_pad)
                 self.G_full = torch.zeros(n_pad, device=dev, dtype=torch.float32)
                 self.Ph_full = torch.zeros(n_pad, device=dev, dtype=torch.float16)
-                self.G, self.Ph = self.G_full[:n], self.Ph_full[:n]
+                self._Gs, self.Ph = [self.G_full[:n]], self.Ph_full[:n]
                 self.G_shard = torch.zeros(n_pad // self.world_size, device=dev, dtype=torch.float32)
             else:
-                self.G = torch.zeros(n, device=dev, dtype=torch.float32)
+                self._Gs = [torch.zeros(n, device=dev, dtype=torch.float32)]
                 self.Ph = torch.empty(n, device=dev, dtype=torch.float16)
             self.M = torch.zeros(n, device=dev, dtype=torch.float32)
             self.V = torch.zeros(n, device=dev, dtype=torch.float32)
@@ -196,7 +247,7 @@ class Trainer:
                     rays_o=torch.zeros(N, 3, **f32), rays_d=torch.zeros(N, 3, **f32), rgb_gt=torch.zeros(N, 3, **f32),
                     noise=torch.zeros(N, **f32), n_samples=torch.zeros(N, **i32), offsets=torch.zeros(N, **i32),
                     counters=torch.zeros(8, **i32), ray_idx=torch.empty(cap, **i32), ts=torch.empty(cap, **f32),
-                    deltas=torch.empty(cap, **f32)))
+                    deltas=torch.empty(cap, **f32), bg=torch.tensor([float(v) for v in bg], **f32)))
             self._cur = 0
             self.stage_t = torch.empty(N * MAX_SAMPLES, **f32)
             self.stage_dt = torch.empty(N * MAX_SAMPLES, **f32)
@@ -230,7 +281,7 @@ class Trainer:
             for st_ in self._sets:
                 b = _lib.NgpTrainBuffers()
                 for name in _SET_FIELDS:
-                    if name != "rgb_gt":
+                    if name not in ("rgb_gt", "bg"):
                         setattr(b, name, st_[name].data_ptr())
                 for name in ("stage_t", "stage_dt", "rgb", "opacity", "depth", "sigmas", "rgbs", "dsigmas", "drgbs",
                              "feat_save", "scalars", "scan_temp"):
@@ -241,6 +292,7 @@ class Trainer:
                 b.scan_temp_bytes = scan_bytes
                 b.bwd_workspace = self.bwd_ws.data_ptr()
                 b.bwd_workspace_bytes = bwd_bytes
+                b.bg_dev = st_["bg"].data_ptr() if self.random_bg else None
                 st_["buf"] = b
 
             # ---- occupancy grid ----------------------------------------------------------------------------
@@ -252,6 +304,8 @@ class Trainer:
             self.gen = torch.Generator(device=dev)
             self.gen.manual_seed(seed + 1000 * self.rank)
         self.graph = False
+        self.graph_launches = 0
+        self._graph_nodes = {}
         self._graph_samples = None
         self._premarched = False
         self._staged = None
@@ -271,15 +325,38 @@ class Trainer:
     def _st(self):
         return torch.cuda.current_stream(self.dev).cuda_stream
 
-    def set_lr(self, lr):
-        self.lr_dev.fill_(float(lr))
+    @property
+    def G(self):
+        """the flat fp32 gradient buffer the step in flight accumulates into (the fused exchange alternates between two)"""
+        return self._Gs[self._gcur]
 
-    def update_density_grid(self, density_threshold=0.01 * MAX_SAMPLES / 3 ** 0.5, warmup=False, decay=0.95):
-        """device-side equivalent of NGP.update_density_grid (reference networks.py:240-269); no host sync"""
+    def set_lr(self, lr):
+        self.lr = float(lr)
+        self.lr_dev.fill_(float(lr))  # stream-ordered, no sync; the Adam kernels read lr from the device
+
+    def sync_params(self):
+        """Call after writing the fp32 parameters from outside (load_state_dict, p.data.copy_, EMA swap...): refreshes the
+        fp16 working copy every kernel reads. In the sharded modes every rank must call it with identical parameters."""
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.lib().ngp_cast_params(self.P.data_ptr(), self.Ph.data_ptr(), self.n_params, self._st()), "cast_params")
+        if self.world_size > 1 and self.ddp in ("p2p", "nvls", "p2p_host", "zero"):
+            import torch.distributed as dist
+            torch.cuda.synchronize(self.dev)
+            dist.barrier(group=self.pg)
+
+    def update_density_grid(self, density_threshold=0.01 * MAX_SAMPLES / 3 ** 0.5, warmup=False, decay=0.95, erode=None):
+        """device-side equivalent of NGP.update_density_grid (reference networks.py:240-269); no host sync.
+        erode (default: the constructor's): per-cell decay from model.count_grid (mark_invisible_cells), networks.py:258-260"""
         m = self.model
+        erode = self.erode if erode is None else erode
+        count = None
+        if erode:
+            if not hasattr(m, "count_grid"):
+                raise RuntimeError("erode=True needs model.count_grid: call model.mark_invisible_cells(K, poses, img_wh) first")
+            count = m.count_grid.data_ptr()
         with torch.cuda.device(self.dev):
             rc = _lib.lib().ngp_update_density_grid(
-                C.byref(self.net), m.density_grid.data_ptr(), m.density_bitfield.data_ptr(), m.cascades, m.grid_size,
+                C.byref(self.net), m.density_grid.data_ptr(), m.density_bitfield.data_ptr(), count, m.cascades, m.grid_size,
                 float(m.scale), float(density_threshold), int(bool(warmup)), float(decay),
                 (self.seed * 2654435761 + self.host_step * 40503 + 12345) & 0xffffffff,
                 self.grid_ws.data_ptr(), self.grid_ws.numel(), self._st())
@@ -321,13 +398,18 @@ class Trainer:
             st_["rays_o"].copy_(rays_o, non_blocking=True)
             st_["rays_d"].copy_(rays_d, non_blocking=True)
             st_["rgb_gt"].copy_(rgb_gt, non_blocking=True)
-            self.g_prepare[nxt].replay()
+            if self.host_step % self.update_interval != 0:
+                # (ahead of a refresh step the march would read the bitfield while the refresh rewrites it, and its result
+                # would be discarded anyway: train_step marches after the refresh)
+                self._replay(self.g_prepare[nxt])
         self._staged = nxt
 
     def march(self, jitter=True):
         """first half of the forward: start jitter + AABB + march + scan + compaction (independent of the weights)"""
         if jitter:
             self.noise.uniform_(0, 1, generator=self.gen)
+        if self.random_bg:
+            self.bg.uniform_(0, 1, generator=self.gen)  # one colour per batch (reference rendering.py:156)
         _lib.check(_lib.lib().ngp_render_train_march(C.byref(self.cfg), C.byref(self.buf), self._st()), "render_train_march")
 
     def network(self):
@@ -365,8 +447,13 @@ class Trainer:
             allreduce_gradients(self.G, self.world_size, self.pg)
 
     def optimizer_step(self):
-        if self.ddp == "p2p":
-            return self._optimizer_step_p2p()
+        """gradient exchange (N > 1) + Adam + fp16 re-cast + clearing of the gradient buffer the next step uses"""
+        if self.ddp in ("p2p", "nvls"):
+            self._launch_fused()
+            self._gcur ^= 1
+            return
+        if self.ddp == "p2p_host":
+            return self._optimizer_step_p2p_host()
         if self.ddp == "zero":
             return self._optimizer_step_zero()
         rc = _lib.lib().ngp_adam_step(self.P.data_ptr(), self.G.data_ptr(), self.M.data_ptr(), self.V.data_ptr(),
@@ -384,8 +471,24 @@ class Trainer:
             _lib.check(rc, "adam_step")
         zero_exchange(self.G_full, self.G_shard, self.Ph_full, self._zero, self.rank, self.world_size, self.pg, adam_on_shard)
 
-    def _optimizer_step_p2p(self):
-        """barrier -> fused reduce-scatter + sharded Adam + all-gather over NVLink -> barrier -> clear own gradients"""
+    def _launch_fused(self):
+        """ONE kernel: start barrier -> reduce-scatter + sharded Adam + all-gather over NVLink (peer loads/stores or
+        multimem) + clear of the other gradient buffer -> end barrier (ngp_adam_step_fused); graph-capturable"""
+        b = self._gcur
+        rc = _lib.lib().ngp_adam_step_fused(self.world_size, self.rank, self.peer_Gs[b], self.peer_Ph, self.peer_flags,
+                                            self.mc_Gs[b], self.mc_Ph, self.P.data_ptr(), self.M.data_ptr(), self.V.data_ptr(),
+                                            self.n_params, self._Gs[1 - b].data_ptr(), self._sync.data_ptr(),
+                                            self.lr_dev.data_ptr(), self.step_dev.data_ptr(), self.betas[0], self.betas[1],
+                                            self.eps, 1, self._st())
+        _lib.check(rc, "adam_step_fused")
+
+    def check_exchange(self):
+        """raises if a fused exchange ever timed out waiting for a peer (synchronises)"""
+        if self.ddp in ("p2p", "nvls") and int(self._sync[2].item()) != 0:
+            raise RuntimeError("ngp_adam_step_fused: a peer did not arrive at a barrier within the timeout")
+
+    def _optimizer_step_p2p_host(self):
+        """round 1: barrier -> reduce-scatter + sharded Adam + all-gather kernel -> barrier -> clear own gradients"""
         self.hG.barrier(channel=0)
         rc = _lib.lib().ngp_adam_step_p2p(self.world_size, self.rank, self.peer_G, self.P.data_ptr(), self.M.data_ptr(),
                                           self.V.data_ptr(), self.peer_Ph, self.n_params, self.lr_dev.data_ptr(),
@@ -395,7 +498,7 @@ class Trainer:
         self.G.zero_()
 
     def shard_bounds(self, rank=None):
-        """[lo, hi) element range of the parameters whose fp32 master / Adam state `rank` owns in p2p mode"""
+        """[lo, hi) element range of the parameters whose fp32 master / Adam state `rank` owns in the sharded modes"""
         r = self.rank if rank is None else rank
         if self.ddp == "zero":
             return zero_shard(self.n_params, self.world_size, r)[:2]
@@ -403,9 +506,9 @@ class Trainer:
         return 4 * lo4, 4 * hi4
 
     def gather_master_params(self):
-        """p2p mode keeps the fp32 master copy of each shard on its owner only: broadcast every shard so that
+        """the sharded modes keep the fp32 master copy of each shard on its owner only: broadcast every shard so that
         state_dict() / checkpoints are complete on every rank (call before saving; synchronises)."""
-        if self.ddp not in ("p2p", "zero"):
+        if self.ddp not in ("p2p", "nvls", "p2p_host", "zero"):
             return
         import torch.distributed as dist
         for r in range(self.world_size):
@@ -437,11 +540,31 @@ class Trainer:
         self._compute()
         self._update()
 
+    def _replay(self, g):
+        self.graph_launches += self._graph_nodes.get(id(g), 0)
+        g.replay()
+
+    def launch_count(self):
+        """kernel launches of libngp_b200 issued for this process so far: eager ones (ngp_launch_count, which also counted
+        every launch recorded while capturing) + recorded launches x graph replays"""
+        return int(_lib.lib().ngp_launch_count()) + self.graph_launches
+
+    def _capture_graph(self, fn):
+        g = torch.cuda.CUDAGraph()
+        g.register_generator_state(self.gen)
+        n0 = int(_lib.lib().ngp_launch_count())
+        with torch.cuda.graph(g):
+            fn()
+        self._graph_nodes[id(g)] = int(_lib.lib().ngp_launch_count()) - n0
+        return g
+
     def capture(self, sample=True):
         """Record the step into CUDA graphs, one [prepare, compute] pair per buffer set plus the optimiser:
-            g_prepare[i] = [device RNG, ngp_gen_rays, march, scan, compaction]          -> writes set i
-            g_compute[i] = [network fwd, compositing, NeRFLoss, compositing bwd, loss scale, MLP bwd, scatter]  reads set i
-            g_update     = [Adam]   (NCCL all-reduce / the p2p kernel and its barriers are launched eagerly)
+            g_prepare[i]    = [device RNG, ngp_gen_rays, march, scan, compaction]          -> writes set i
+            g_compute[i][b] = [network fwd, compositing, NeRFLoss, compositing bwd, loss scale, MLP bwd, scatter]
+                              reads set i, accumulates into gradient buffer b
+            g_update[b]     = [Adam], or for N > 1 the self-synchronising exchange kernel reducing buffer b and clearing
+                              buffer 1-b (the NCCL modes launch their collectives eagerly)
         The front of a step (batch assembly + march) depends on the rays, the jitter and the occupancy bitfield but
         NOT on the weights, so train_step() replays the NEXT step's g_prepare into the other buffer set on a side
         stream while this step's g_compute and g_update run on the main stream (except across an occupancy refresh,
@@ -449,35 +572,40 @@ class Trainer:
         dev = self.dev
         s = torch.cuda.Stream(dev)
         s.wait_stream(torch.cuda.current_stream(dev))
+        state = [self.P, self.M, self.V, self.Ph, self.step_dev] + list(self._Gs)
         with torch.cuda.stream(s):
             # one eager run so lazy initialisation (cudaFuncSetAttribute, NCCL / symmetric-memory setup) is done
-            saved = [t.clone() for t in (self.P, self.M, self.V, self.Ph, self.G, self.step_dev)]
+            saved = [t.clone() for t in state]
+            gcur = self._gcur
             self._step_body(sample)
-            if self.ddp == "p2p":
+            if self.ddp == "p2p_host":
                 self.hG.barrier(channel=0)
-            for t, v in zip((self.P, self.M, self.V, self.Ph, self.G, self.step_dev), saved):
+            for t, v in zip(state, saved):
                 t.copy_(v)
-            if self.ddp == "p2p":
+            self._gcur = gcur
+            if self.ddp == "p2p_host":
                 self.hG.barrier(channel=0)
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
         self.g_prepare, self.g_compute, self.g_update = [], [], None
-        keep = self._cur
+        keep = (self._cur, self._gcur)
         for i in range(2):
             self._cur = i
-            gp, gc = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            gp.register_generator_state(self.gen)
-            with torch.cuda.graph(gp):
-                self._prepare(sample)
-            with torch.cuda.graph(gc):
-                self._compute()
-            self.g_prepare.append(gp)
-            self.g_compute.append(gc)
-        self._cur = keep
-        if self.ddp not in ("p2p", "zero"):
-            self.g_update = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.g_update):
-                self.optimizer_step()
+            self.g_prepare.append(self._capture_graph(lambda: self._prepare(sample)))
+            per_buf = []
+            for b in range(self._n_gbuf):
+                self._gcur = b
+                per_buf.append(self._capture_graph(self._compute))
+            self.g_compute.append(per_buf)
+        if self.ddp in ("p2p", "nvls"):
+            self.g_update = []
+            for b in range(self._n_gbuf):
+                self._gcur = b
+                self.g_update.append(self._capture_graph(self._launch_fused))
+        elif self.ddp not in ("p2p_host", "zero"):
+            self._gcur = 0
+            self.g_update = [self._capture_graph(self.optimizer_step)]
+        self._cur, self._gcur = keep
         self.graph = True
         self._graph_samples = sample
         self._side = torch.cuda.Stream(dev)
@@ -487,10 +615,26 @@ class Trainer:
         self._inflight = False
         self._premarched = False
 
+    def _graph_update(self):
+        """the optimiser half of a captured step on the main stream"""
+        self.allreduce()
+        if self.g_update is None:
+            self.optimizer_step()
+            return
+        self._replay(self.g_update[self._gcur])
+        if self._n_gbuf == 2:
+            self._gcur ^= 1
+
     def train_step(self, sample=True):
         """one full training step incl. the occupancy refresh cadence of reference train.py:160-163"""
+        if self.lr_schedule is not None:
+            lr = self.lr_schedule.lr_at_step(self.host_step)
+            if lr != self.lr:
+                self.set_lr(lr)
         refresh = self.host_step % self.update_interval == 0
         if refresh:
+            if self._staged is not None:
+                torch.cuda.current_stream(self.dev).wait_stream(self._side)  # a staged copy may still be in flight
             self.update_density_grid(warmup=self.host_step < self.warmup_steps)
         if not (self.graph and self._graph_samples == sample):
             self._step_body(sample)
@@ -498,35 +642,25 @@ class Trainer:
             self.host_step += 1
             return
         main = torch.cuda.current_stream(self.dev)
-        if self._staged is not None:  # a host batch staged (copied + marched) by stage_batch()
+        if self._staged is not None:  # a host batch staged (copied [+ marched]) by stage_batch()
             self._cur = self._staged
             self._staged = None
             main.wait_stream(self._side)
-            if refresh:  # marched against the previous bitfield: same rays and jitter again, like the reference's ordering
-                _lib.check(_lib.lib().ngp_render_train_march(C.byref(self.cfg), C.byref(self.buf), self._st()),
-                           "render_train_march")
-            self.g_compute[self._cur].replay()
+            if refresh:  # staged ahead of a refresh: march now, against the refreshed grid (the reference's ordering)
+                self._replay(self.g_prepare[self._cur])
+            self._replay(self.g_compute[self._cur][self._gcur])
             if self._ev_set[self._cur] is None:
                 self._ev_set[self._cur] = torch.cuda.Event()
             self._ev_set[self._cur].record(main)
-            self.allreduce()
-            if self.g_update is not None:
-                self.g_update.replay()
-            else:
-                self.optimizer_step()
+            self._graph_update()
             self._premarched = False
             self._inflight = True
             self.host_step += 1
             return
         if self._premarched:
             self._cur = 1 - self._cur  # the set the previous step marched ahead
-            if refresh:
-                # (not reached with the cadence below) marched against the previous bitfield: march the SAME rays and
-                # jitter again so that the step sees the refreshed grid, exactly like the reference's ordering
-                _lib.check(_lib.lib().ngp_render_train_march(C.byref(self.cfg), C.byref(self.buf), self._st()),
-                           "render_train_march")
         else:
-            self.g_prepare[self._cur].replay()
+            self._replay(self.g_prepare[self._cur])
         # deep pipeline: the next step's batch + march into the OTHER set (side stream) under this whole step
         ahead = sample and ((self.host_step + 1) % self.update_interval != 0)
         if ahead:
@@ -537,14 +671,10 @@ class Trainer:
             else:
                 self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
-                self.g_prepare[1 - self._cur].replay()
-        self.g_compute[self._cur].replay()
+                self._replay(self.g_prepare[1 - self._cur])
+        self._replay(self.g_compute[self._cur][self._gcur])
         self._ev_compute.record(main)
-        self.allreduce()
-        if self.g_update is not None:
-            self.g_update.replay()
-        else:
-            self.optimizer_step()
+        self._graph_update()
         if ahead:
             main.wait_stream(self._side)
         self._premarched = ahead

@@ -4,7 +4,7 @@ INFRASTRUCTURE ONLY.
     ref = load_reference()            # ref.vren, ref.NGP, ref.render, ref.custom_functions, ref.losses
 runs the reference's own models/{custom_functions,networks,rendering}.py with
     vren        = the reference's CUDA extension compiled from /root/reference/models/csrc
-    tinycudann  = oracle/tcnn_standin.py (tinycudann itself is unavailable, see that file)
+    tinycudann  = oracle/tcnn_standin.py (checker) or oracle/tcnn_fast.py (performance-grade); tinycudann itself is unavailable
     torch_scatter.segment_csr = a torch restatement (only used when rays are optimised)
 Needs a GPU to *run* (the reference has no CPU path).
 """
@@ -33,11 +33,14 @@ def python_available():
 _cached = {}
 
 
-def load_reference(drop_in=False):
-    """drop_in=False: the reference's Python on the REFERENCE's compiled vren + the tinycudann stand-in.
+def load_reference(drop_in=False, tcnn="standin"):
+    """drop_in=False: the reference's Python on the REFERENCE's compiled vren + a tinycudann stand-in:
+                   tcnn="standin" the checker-grade restatement (oracle/tcnn_standin.py),
+                   tcnn="fast"    the performance-grade one (oracle/tcnn_fast.py; what `bench.py --impl reference` times).
     drop_in=True : the reference's Python on ngp_pl_b200.vren + ngp_pl_b200.tcnn (the drop-in claim under test)."""
-    if drop_in in _cached:
-        return _cached[drop_in]
+    key = (drop_in, tcnn)
+    if key in _cached:
+        return _cached[key]
     import torch  # noqa: F401  (must be imported before the extension)
     if drop_in:
         if not python_available():
@@ -59,8 +62,11 @@ def load_reference(drop_in=False):
         if "vren" in sys.modules and getattr(sys.modules["vren"], "__file__", "") and "ngp_pl_b200" in sys.modules["vren"].__file__:
             del sys.modules["vren"]
         vren = importlib.import_module("vren")
-        from . import tcnn_standin
-        sys.modules["tinycudann"] = tcnn_standin
+        if tcnn == "fast":
+            from . import tcnn_fast as tcnn_mod
+        else:
+            from . import tcnn_standin as tcnn_mod
+        sys.modules["tinycudann"] = tcnn_mod
     ts = types.ModuleType("torch_scatter")
 
     def segment_csr(src, indptr):
@@ -95,5 +101,5 @@ def load_reference(drop_in=False):
             sys.modules.pop(k, None)
         else:
             sys.modules[k] = v
-    _cached[drop_in] = r
+    _cached[key] = r
     return r

@@ -297,19 +297,23 @@ def test_warp_marcher_bit_exact_vs_oracle(name, oracle):
 
 
 def test_fused_nvlink_optimizer_step_two_gpus(tmp_path):
-    """ngp_adam_step_p2p (reduce-scatter + sharded Adam + all-gather over NVLink peer memory) == NCCL all-reduce +
-    full Adam, bitwise at N=2 (tools/check_p2p.py under torchrun). Needs two GPUs; skipped on a 1-GPU box."""
+    """ngp_adam_step_fused / ngp_adam_step_p2p (reduce-scatter + sharded Adam + all-gather over NVLink peer memory, with
+    in-kernel or host barriers, with or without NVLS multicast) == NCCL all-reduce + full Adam, bitwise at N=2
+    (tools/check_p2p.py under torchrun). Needs two GPUs; skipped on a 1-GPU box (bench.py's N>1 runs repeat the check on
+    their first step and report it in the JSON line as `exchange_check`)."""
     import os
     import subprocess
     import sys
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(root, "tools", "check_p2p.py")],
-                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-3000:]
-    assert "MISMATCH" not in r.stdout
+    for k, mode in enumerate(("p2p", "nvls", "p2p_host")):
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                            "--master-addr", "127.0.0.1", "--master-port", str(29541 + k),
+                            os.path.join(root, "tools", "check_p2p.py"), mode],
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-3000:]
+        assert "MISMATCH" not in r.stdout
 
 
 def test_fused_trainer_with_distortion_loss_matches_autograd():

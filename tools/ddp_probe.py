@@ -1,6 +1,6 @@
 """Per-phase timing of the multi-GPU step (run under torchrun on one node):
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/ddp_probe.py [p2p|zero|nccl] [steps]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/ddp_probe.py [p2p|nvls|p2p_host|zero|nccl] [steps]
 
 Every rank trains the synthetic Lego scene like bench.py, then times -- with CUDA events on its own stream -- the pieces of
 the step in isolation (compute graph, each collective / barrier / kernel of the optimiser exchange) and the pipelined
@@ -30,7 +30,14 @@ def main():
     scene = synth.lego_scene(0)
     bank = synth.RayBank(scene, n_images=100, device=dev, seed=rank)
     model = NGP(scene.scale).to(dev)
-    tr = Trainer(model, n_rays=8192, lr=1e-2, process_group=None, world_size=world, rank=rank, seed=rank, ddp=mode)
+    try:
+        tr = Trainer(model, n_rays=8192, lr=1e-2, process_group=None, world_size=world, rank=rank, seed=rank, ddp=mode)
+    except RuntimeError as e:
+        if rank == 0:
+            print(json.dumps({"mode": mode, "world": world, "unavailable": str(e)}))
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     tr.attach_bank(bank)
     tr.capture(sample=True)
     for _ in range(steps):
@@ -55,9 +62,14 @@ def main():
 
     res = {}
     cur = tr._cur
-    res["compute_graph_us"] = timed(tr.g_compute[cur].replay)
+    res["compute_graph_us"] = timed(lambda: tr.g_compute[cur][tr._gcur].replay())
     res["prepare_graph_us"] = timed(tr.g_prepare[cur].replay)
-    if mode == "p2p":
+    if mode in ("p2p", "nvls"):
+        # the self-synchronising exchange kernel (start barrier + reduce-scatter/Adam/all-gather + clear + end barrier);
+        # ranks enter together (timed() barriers first), so this is the kernel's own time
+        res["fused_exchange_us"] = timed(tr._graph_update)
+        res["fused_exchange_skewed_us"] = timed(tr._graph_update, sync_ranks=False)
+    elif mode == "p2p_host":
         res["barrier_us"] = timed(lambda: tr.hG.barrier(channel=0))
         L = _lib.lib()
 
@@ -76,8 +88,8 @@ def main():
         res["all_gather_us"] = timed(lambda: dist.all_gather_into_tensor(tr.Ph_full, tr.Ph_full[lo:lo + shard]))
     else:
         res["all_reduce_us"] = timed(lambda: dist.all_reduce(tr.G))
-        res["adam_graph_us"] = timed(tr.g_update.replay)
-    res["optimizer_step_us"] = timed(lambda: (tr.allreduce(), tr.g_update.replay() if tr.g_update is not None else tr.optimizer_step()))
+        res["adam_graph_us"] = timed(tr.g_update[0].replay)
+    res["optimizer_step_us"] = timed(tr._graph_update)
     # the pipelined step, ranks free-running (what bench.py measures)
     torch.cuda.synchronize()
     dist.barrier()
@@ -98,7 +110,7 @@ def main():
     if rank == 0:
         m = torch.stack(allt).cpu()
         out = {k: {"min": float(m[:, i].min()), "mean": float(m[:, i].mean()), "max": float(m[:, i].max())} for i, k in enumerate(keys)}
-        print(json.dumps({"mode": mode, "world": world, "phases": out}, indent=1))
+        print(json.dumps({"mode": mode, "world": world, "phases": out}))
     dist.destroy_process_group()
 
 

@@ -90,7 +90,7 @@ def in_context(fns, n=40):
 
 cur = tr._cur
 fwd_p, loss_p, bwd_p = piece(tr.network), piece(loss_only), piece(bwd_only)
-C_ = tr.g_compute[cur].replay
+C_ = tr.g_compute[cur][0].replay
 
 
 def seq3():
@@ -103,6 +103,6 @@ print("V5 t(fwd) t(loss) t(bwd)    ", t(fwd_p, 200), t(loss_p, 200), t(bwd_p, 20
 print("V3 in_context([C])          ", in_context([C_], 100))
 print("V4 in_context([fwd,loss,bwd])", in_context([fwd_p, loss_p, bwd_p], 100))
 print("V6 in_context([fwd,bwd])    ", in_context([fwd_p, bwd_p], 100))
-print("V7 in_context([C,U])        ", in_context([C_, tr.g_update.replay], 100))
-print("V8 t(C;U)                   ", t(lambda: (C_(), tr.g_update.replay()), 200))
+print("V7 in_context([C,U])        ", in_context([C_, tr.g_update[0].replay], 100))
+print("V8 t(C;U)                   ", t(lambda: (C_(), tr.g_update[0].replay()), 200))
 print("stats", tr.stats())

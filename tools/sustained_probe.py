@@ -59,14 +59,14 @@ def run(name, fn, n):
 
 
 def cu():
-    tr.g_compute[cur].replay()
-    tr.g_update.replay()
+    tr.g_compute[cur][0].replay()
+    tr.g_update[0].replay()
 
 
 for n in (50, 300, 2000):
-    run("C", tr.g_compute[cur].replay, n)
+    run("C", tr.g_compute[cur][0].replay, n)
 for n in (50, 300, 2000):
-    run("U", tr.g_update.replay, n)
+    run("U", tr.g_update[0].replay, n)
 for n in (50, 300, 2000):
     run("C;U", cu, n)
 for n in (50, 300, 2000):
