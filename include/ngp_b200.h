@@ -370,10 +370,13 @@ typedef struct {
 
 size_t ngp_render_infer_workspace(int n_rays, int64_t max_round_samples); /* workspace of ngp_render_infer */
 /* Runs rounds [first_round, first_round+n_rounds) of the wavefront (first_round == 0 initialises; finish != 0
- * adds the background and writes total_samples). Per round every alive ray takes up to
- * min(2,2,4,4,...,64 schedule, max_round_samples / n_alive) samples. alive_count_out (device int32*, optional)
- * gets the number of rays still alive afterwards -- reading it back every few rounds is the only host
- * synchronisation of the path. Requires max_round_samples >= n_rays. */
+ * adds the background and writes total_samples). Per round every alive ray takes up to the reference's quota
+ * N_samples = max(min(n_rays / n_alive, 64), min_samples) (rendering.py:73,80; min_samples = 1 if exp_step_factor == 0
+ * else 4), evaluated on the device from the alive count; the alive-list rules are composite_test_fw's
+ * (volumerendering.cu:221-248), so total_samples reproduces the operator loop's. alive_count_out (device int32*,
+ * optional) gets the number of rays still alive afterwards -- reading it back every few rounds is the only host
+ * synchronisation of the path. Requires max_round_samples >= 4 * n_rays for the quota never to be clipped
+ * (>= n_rays to run at all). */
 int ngp_render_infer(const NgpNet* net, const NgpInferCfg* cfg, const float* rays_o, const float* rays_d,
                      const uint8_t* density_bitfield, float* opacity, float* depth, float* rgb, int64_t* total_samples,
                      int first_round, int n_rounds, int finish, int* alive_count_out,

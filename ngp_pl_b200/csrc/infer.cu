@@ -18,50 +18,43 @@
 #include "../../include/ngp_b200.h"
 
 
-// init: AABB (+ near clamp), zero the accumulators, build the first alive list
+// init: AABB (+ near clamp), zero the accumulators. EVERY ray enters the first alive list, in order, like the reference's
+// alive_indices = arange(N_rays) (rendering.py:71): rays that miss the box take no sample in round 0 and are dropped by
+// its compositing (composite_test_fw: N_eff == 0 -> not alive), so the per-round quota N_rays // N_alive of the following
+// rounds sees the same alive counts as the reference's loop.
 __global__ void k_infer_init(const NgpInferCfg cfg, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                              float* __restrict__ t_cur, float* __restrict__ t_end, float* __restrict__ opacity,
                              float* __restrict__ depth, float* __restrict__ rgb, int* __restrict__ alive,
                              int* __restrict__ alive_count) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    bool hit = false;
-    if (r < cfg.n_rays) {
-        const MarchRay ray = make_march_ray(rays_o[3 * r], rays_o[3 * r + 1], rays_o[3 * r + 2],
-                                            rays_d[3 * r], rays_d[3 * r + 1], rays_d[3 * r + 2]);
-        const float2 tt = ray_aabb(ray, cfg.center[0], cfg.center[1], cfg.center[2], cfg.half_size[0], cfg.half_size[1],
-                                   cfg.half_size[2]);
-        float t1 = -1.0f, t2 = -1.0f;
-        if (tt.y > 0.0f) {
-            t1 = fmaxf(tt.x, 0.0f);
-            t2 = tt.y;
-        }
-        if (t1 >= 0.0f && t1 < cfg.near_distance) t1 = cfg.near_distance;
-        t_cur[r] = t1;
-        t_end[r] = t2;
-        opacity[r] = 0.f;
-        depth[r] = 0.f;
-        rgb[3 * r] = 0.f; rgb[3 * r + 1] = 0.f; rgb[3 * r + 2] = 0.f;
-        hit = t1 >= 0.0f && t1 < t2;
+    if (r == 0) *alive_count = cfg.n_rays;
+    if (r >= cfg.n_rays) return;
+    const MarchRay ray = make_march_ray(rays_o[3 * r], rays_o[3 * r + 1], rays_o[3 * r + 2],
+                                        rays_d[3 * r], rays_d[3 * r + 1], rays_d[3 * r + 2]);
+    const float2 tt = ray_aabb(ray, cfg.center[0], cfg.center[1], cfg.center[2], cfg.half_size[0], cfg.half_size[1],
+                               cfg.half_size[2]);
+    float t1 = -1.0f, t2 = -1.0f;
+    if (tt.y > 0.0f) {
+        t1 = fmaxf(tt.x, 0.0f);
+        t2 = tt.y;
     }
-    // warp-aggregated append
-    const unsigned m = __ballot_sync(0xffffffffu, hit);
-    if (m) {
-        int base = 0;
-        const int leader = __ffs(m) - 1;
-        if (lane == leader) base = atomicAdd(alive_count, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (hit) alive[base + __popc(m & ((1u << lane) - 1u))] = r;
-    }
+    if (t1 >= 0.0f && t1 < cfg.near_distance) t1 = cfg.near_distance;
+    t_cur[r] = t1;
+    t_end[r] = t2;
+    opacity[r] = 0.f;
+    depth[r] = 0.f;
+    rgb[3 * r] = 0.f; rgb[3 * r + 1] = 0.f; rgb[3 * r + 2] = 0.f;
+    alive[r] = r;
 }
 
-// per-round bookkeeping (1 thread): fair share of the sample buffers, budget accounting, counter reset.
-//   S_eff = clamp(capacity / n_alive, 1, S_sched)   (the reference's N_samples = min(N_rays // N_alive, 64) idea,
-//   rendering.py:80, so n_alive * S_eff always fits);  once the requested total reaches the reference's
-//   loop budget (`max_samples` kwarg, rendering.py:75) the remaining rays are dropped, as its loop exit does.
-// state: [0] S_eff  [1] requested so far  [2] sample count of this round  [3] rounds run
-__global__ void k_infer_round_begin(const NgpInferCfg cfg, const int S_sched, int* __restrict__ alive_count,
-                                    int* __restrict__ next_count, int* __restrict__ state, int64_t* __restrict__ total) {
+// per-round bookkeeping (1 thread), the head of the reference's loop (rendering.py:75-81):
+//   while samples < max_samples:  N_alive = len(alive); if N_alive == 0: break
+//       N_samples = max(min(N_rays // N_alive, 64), min_samples);  samples += N_samples
+// computed from the device-side alive count. N_alive * N_samples <= max(N_rays, min_samples * N_alive) <= 4 * N_rays, the
+// capacity of the per-round sample buffers (max_round_samples), so the quota never has to be clipped.
+// state: [0] N_samples of this round (0 = loop over)  [1] `samples` so far  [2] sample count of this round  [3] rounds run
+__global__ void k_infer_round_begin(const NgpInferCfg cfg, int* __restrict__ alive_count, int* __restrict__ next_count,
+                                    int* __restrict__ state, int64_t* __restrict__ total) {
     *total += state[2];
     state[2] = 0;
     *next_count = 0;
@@ -70,9 +63,11 @@ __global__ void k_infer_round_begin(const NgpInferCfg cfg, const int S_sched, in
         n_alive = 0;
         *alive_count = 0;
     }
-    int S = S_sched;
+    int S = 0;
     if (n_alive > 0) {
-        const int64_t share = cfg.max_round_samples / n_alive;
+        const int min_samples = cfg.exp_step_factor == 0.0f ? 1 : 4;
+        S = max(min(cfg.n_rays / n_alive, 64), min_samples);
+        const int64_t share = cfg.max_round_samples / n_alive;  // (never binds for max_round_samples >= 4 * n_rays)
         if (share < S) S = (int)(share < 1 ? 1 : share);
         state[1] += S;
         state[3] += 1;
@@ -179,8 +174,10 @@ __global__ void k_infer_composite(const NgpInferCfg cfg, const float* __restrict
         opacity[r] = o;
         depth[r] = d;
         rgb[3 * r] = cr; rgb[3 * r + 1] = cg; rgb[3 * r + 2] = cb;
-        // alive while not converged and still inside the box
-        keep = !term && (t_cur[r] < t_end[r]);
+        // the reference's rule (composite_test_fw, volumerendering.cu:221-224,:245-248): a ray leaves the alive list when it
+        // got no sample this round or its transmittance fell to the threshold -- a ray that ran out of box with SOME samples
+        // stays for one more (empty) round, and counts in that round's N_alive
+        keep = !term && n > 0;
     }
     const unsigned m = __ballot_sync(0xffffffffu, keep);
     if (m) {
@@ -203,11 +200,7 @@ __global__ void k_infer_finish(const NgpInferCfg cfg, const float* __restrict__ 
     rgb[3 * r + 2] += cfg.bg[2] * rest;
 }
 
-static int round_samples(int round) {
-    // 2,2,4,4,8,8,16,16,32,32,64,64,...
-    const int e = 1 + round / 2;
-    return e >= 6 ? 64 : (1 << e);
-}
+#define INFER_S_MAX 64  // the reference's cap on N_samples (rendering.py:80)
 
 extern "C" size_t ngp_render_infer_workspace(int n_rays, int64_t max_round_samples) {
     if (n_rays < 1 || max_round_samples < 1) return 0;
@@ -261,12 +254,12 @@ extern "C" int ngp_render_infer(const NgpNet* net, const NgpInferCfg* cfg, const
         NGP_CHECK_LAUNCH();
     }
     for (int round = first_round; round < first_round + n_rounds; ++round) {
-        const int S = round_samples(round);
+        const int S = INFER_S_MAX;  // staging capacity; the round's actual quota is computed on the device
         const int cur = round & 1, nxt = cur ^ 1;
         const int bs = 64;
         // the launch covers the worst case (all rays alive); blocks past the device-side count exit at once
         const int grid = ngp_div_up(n, bs);
-        k_infer_round_begin<<<1, 1, 0, st>>>(*cfg, S, alive_cnt + cur, alive_cnt + nxt, state, total);
+        k_infer_round_begin<<<1, 1, 0, st>>>(*cfg, alive_cnt + cur, alive_cnt + nxt, state, total);
         NGP_CHECK_LAUNCH();
         k_infer_march<<<grid, bs, (size_t)bs * S * sizeof(float2), st>>>(
             *cfg, S, rays_o, rays_d, density_bitfield, t_cur, t_end, alive[cur], alive_cnt + cur, ray_start, ray_n,

@@ -45,10 +45,16 @@ RaySphereIntersector.__name__ = RaySphereIntersector.__qualname__ = "RaySphereIn
 
 
 def _sum_per_ray(per_sample, rays_a):
-    """(S, C) per-sample values -> (N, C) per-ray sums; rays_a rows are [ray, first sample, count] in ray order and the samples
-    of a ray are contiguous (the reference uses torch_scatter.segment_csr on the same offsets)."""
-    n_rays = rays_a.shape[0]
-    owner = torch.repeat_interleave(torch.arange(n_rays, device=per_sample.device), rays_a[:, 2])
+    """(S, C) per-sample values -> (N, C) per-ray sums, row r = the ray rays_a[r, 0]. rays_a rows are [ray, first sample, count]
+    in ANY row order (the reference's marcher emits them in atomic order); a ray's samples are contiguous from its first
+    sample. The reference uses torch_scatter.segment_csr on the same offsets (custom_functions.py:107-110), which
+    additionally assumes rows sorted by first sample; this version does not."""
+    n_rays, S = rays_a.shape[0], per_sample.shape[0]
+    # owner row of every sample: +1 at each non-empty row's first sample (in sample order), running count - 1
+    order = torch.argsort(rays_a[:, 1], stable=True)
+    counts = rays_a[order, 2]
+    owner_sorted = torch.repeat_interleave(torch.arange(n_rays, device=per_sample.device), counts, output_size=S)
+    owner = rays_a[order, 0][owner_sorted]
     return torch.zeros(n_rays, per_sample.shape[1], device=per_sample.device, dtype=per_sample.dtype).index_add_(0, owner, per_sample)
 
 

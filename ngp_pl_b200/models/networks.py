@@ -63,6 +63,12 @@ class _NGPForward(torch.autograd.Function):
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, x, d, enc_params, rgb_params, model):
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            # tinycudann also returns dL/dx through the hash grid (and dL/dd through SH); the reference needs it only for
+            # --optimize_ext (learned pose corrections, train.py:88-91). Not built here: fail loudly instead of silently
+            # handing zero gradients to RayMarcher.backward.
+            raise NotImplementedError("ngp_pl_b200: gradients w.r.t. sample positions / directions (pose refinement, "
+                                      "reference --optimize_ext) are not implemented; detach x and d")
         x = x.contiguous()
         d = d.contiguous()
         n = x.shape[0]
@@ -138,6 +144,9 @@ class _DensityFeatures(torch.autograd.Function):
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, x01, params, module):
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("ngp_pl_b200: dL/dx through the hash grid (reference --optimize_ext) is not implemented; "
+                                      "detach the positions")
         x01 = x01.float().contiguous()  # (cast_inputs only acts under autocast)
         n, dev = x01.shape[0], x01.device
         with torch.cuda.device(dev):

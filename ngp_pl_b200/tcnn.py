@@ -28,11 +28,17 @@ def _st():
 
 
 class _HalfCopy:
-    """fp16 working copy of an fp32 parameter vector, refreshed when the parameter changes
-    (tinycudann re-casts every forward)."""
+    """fp16 working copy of an fp32 parameter vector. tinycudann re-casts its parameters on every forward; so does this
+    whenever the parameter can have changed behind autograd's back: always while it requires grad and grad mode is on (an
+    optimiser that writes through `p.data` -- apex FusedAdam, the reference's choice at train.py:128-134 -- or an EMA swap
+    does NOT bump `p._version`), otherwise (inference) only when (pointer, version) changed. ~25 us for the 11.5 M
+    parameters. `invalidate()` forces the next call to re-cast."""
 
     def __init__(self):
         self.buf = None
+        self.key = None
+
+    def invalidate(self):
         self.key = None
 
     def get(self, p):
@@ -40,7 +46,7 @@ class _HalfCopy:
         if self.buf is None or self.buf.device != p.device or self.buf.numel() != p.numel():
             self.buf = torch.empty(p.numel(), device=p.device, dtype=torch.float16)
             self.key = None
-        if key != self.key:
+        if key != self.key or (p.requires_grad and torch.is_grad_enabled()):
             with torch.cuda.device(p.device):
                 _lib.check(_lib.lib().ngp_cast_params(p.data_ptr(), self.buf.data_ptr(), p.numel(), _st()), "cast_params")
             self.key = key
@@ -48,10 +54,14 @@ class _HalfCopy:
 
 
 class _FixedHalf:
-    """fp16 working copy owned by someone else (the Trainer's flat buffer, refreshed by its Adam kernel)"""
+    """fp16 working copy owned by someone else (the Trainer's flat buffer, refreshed by its Adam kernel; after an outside
+    write to the fp32 parameters -- load_state_dict, p.data.copy_ -- call Trainer.sync_params())"""
 
     def __init__(self, buf):
         self.buf = buf
+
+    def invalidate(self):
+        pass
 
     def get(self, p):
         return self.buf

@@ -303,6 +303,8 @@ class Trainer:
             self.grid_ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
             self.gen = torch.Generator(device=dev)
             self.gen.manual_seed(seed + 1000 * self.rank)
+        # model.load_state_dict(...) writes the fp32 parameters behind the kernels' back: refresh the fp16 working copy
+        self._load_hook = model.register_load_state_dict_post_hook(lambda module, incompatible: self.sync_params())
         self.graph = False
         self.graph_launches = 0
         self._graph_nodes = {}

@@ -237,8 +237,9 @@ def test_fused_inference_matches_operator_loop(which):
         err = (a[k] - b[k]).abs()
         assert err.max().item() < 2e-4 * max(1.0, b[k].abs().max().item()), "%s: max err %g" % (k, err.max().item())
     ta, tb = int(a["total_samples"]), int(b["total_samples"])
-    # the loop marches in chunks too; chunk sizes differ, so the marched (not composited) totals differ slightly
-    assert ta > 0 and abs(ta - tb) < 0.35 * tb
+    # both evaluate the reference's per-round quota max(min(N_rays // N_alive, 64), min_samples) (rendering.py:80) from the same
+    # alive counts, so the marched totals agree up to the rays whose termination round moves with the last bits of sigma
+    assert ta > 0 and abs(ta - tb) <= 0.01 * tb
 
 
 def test_training_converges_and_graph_capture_works():
