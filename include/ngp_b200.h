@@ -382,6 +382,17 @@ int ngp_render_infer(const NgpNet* net, const NgpInferCfg* cfg, const float* ray
                      int first_round, int n_rounds, int finish, int* alive_count_out,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same wavefront for a WHOLE frame as one CUDA graph with a device-side loop (a conditional WHILE node whose
+ * condition a kernel sets from the alive count): init -> while (rays alive and samples < sample_budget) { round } ->
+ * finish. One graph launch per call, no host read-back at all (the reference's loop synchronises >= 3 times per round,
+ * rendering.py:75-105). The instantiated graph is cached per (device, every pointer argument, *net, *cfg) -- up to 8
+ * entries, rebuilt on a miss (~1 ms) -- so callers should render from the same buffers frame after frame. Not thread-safe.
+ * Returns a cudaError_t if the driver cannot build conditional graph nodes (callers may then fall back to
+ * ngp_render_infer). */
+int ngp_render_infer_frame(const NgpNet* net, const NgpInferCfg* cfg, const float* rays_o, const float* rays_d,
+                           const uint8_t* density_bitfield, float* opacity, float* depth, float* rgb, int64_t* total_samples,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -153,6 +153,7 @@ SIGNATURES = {
     "ngp_render_infer_workspace": (_sz, [_i, _i64]),
     "ngp_render_infer": (_i, [C.POINTER(NgpNet), C.POINTER(NgpInferCfg), _P, _P, _P, _P, _P, _P, _P, _i, _i, _i, _P,
                               _P, _sz, _P]),
+    "ngp_render_infer_frame": (_i, [C.POINTER(NgpNet), C.POINTER(NgpInferCfg), _P, _P, _P, _P, _P, _P, _P, _P, _sz, _P]),
     "ngp_update_grid_workspace": (_sz, [_i, _i]),
     "ngp_update_density_grid": (_i, [C.POINTER(NgpNet), _P, _P, _P, _i, _i, _f, _f, _i, _f, C.c_uint32, _P, _sz, _P]),
 }

@@ -16,7 +16,7 @@
 #include "common.cuh"
 #include "march.cuh"
 #include "../../include/ngp_b200.h"
-
+#include <string.h>
 
 // init: AABB (+ near clamp), zero the accumulators. EVERY ray enters the first alive list, in order, like the reference's
 // alive_indices = arange(N_rays) (rendering.py:71): rays that miss the box take no sample in round 0 and are dropped by
@@ -202,6 +202,41 @@ __global__ void k_infer_finish(const NgpInferCfg cfg, const float* __restrict__ 
 
 #define INFER_S_MAX 64  // the reference's cap on N_samples (rendering.py:80)
 
+struct InferWs {
+    float *t_cur, *t_end;
+    int* alive[2];
+    int *ray_start, *ray_n, *ray_idx;
+    float *ts, *deltas, *sigmas, *rgbs;
+    int *counters, *alive_cnt, *state;
+    int64_t* total;
+};
+static InferWs infer_ws(const NgpInferCfg* cfg, void* workspace) {
+    const size_t nr = ((size_t)cfg->n_rays * 4 + 255) & ~(size_t)255;
+    const size_t ns = ((size_t)cfg->max_round_samples * 4 + 255) & ~(size_t)255;
+    char* w = (char*)workspace;
+    InferWs W;
+    W.t_cur = (float*)w; w += nr;
+    W.t_end = (float*)w; w += nr;
+    W.alive[0] = (int*)w; w += nr;
+    W.alive[1] = (int*)w; w += nr;
+    W.ray_start = (int*)w; w += nr;
+    W.ray_n = (int*)w; w += nr;
+    W.ray_idx = (int*)w; w += ns;
+    W.ts = (float*)w; w += ns;
+    W.deltas = (float*)w; w += ns;
+    W.sigmas = (float*)w; w += ns;
+    W.rgbs = (float*)w; w += 3 * ns;
+    W.counters = (int*)w;  // [0],[1] alive counts (ping-pong)  [8..11] state  [16..17] int64 total
+    W.alive_cnt = W.counters;
+    W.state = W.counters + 8;
+    W.total = (int64_t*)(W.counters + 16);
+    return W;
+}
+
+// one round of the wavefront on stream st; the ping-pong role of the two alive lists is given by `cur`
+static int infer_round(const NgpNet* net, const NgpInferCfg* cfg, const InferWs& W, const float* rays_o, const float* rays_d,
+                       const uint8_t* density_bitfield, float* opacity, float* depth, float* rgb, int cur, cudaStream_t st);
+
 extern "C" size_t ngp_render_infer_workspace(int n_rays, int64_t max_round_samples) {
     if (n_rays < 1 || max_round_samples < 1) return 0;
     const size_t nr = ((size_t)n_rays * 4 + 255) & ~(size_t)255;
@@ -227,52 +262,21 @@ extern "C" int ngp_render_infer(const NgpNet* net, const NgpInferCfg* cfg, const
     if (workspace_bytes < ngp_render_infer_workspace(cfg->n_rays, cfg->max_round_samples)) return NGP_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     const int n = cfg->n_rays;
-    const size_t nr = ((size_t)n * 4 + 255) & ~(size_t)255;
-    const size_t ns = ((size_t)cfg->max_round_samples * 4 + 255) & ~(size_t)255;
-    char* w = (char*)workspace;
-    float* t_cur = (float*)w; w += nr;
-    float* t_end = (float*)w; w += nr;
-    int* alive[2];
-    alive[0] = (int*)w; w += nr;
-    alive[1] = (int*)w; w += nr;
-    int* ray_start = (int*)w; w += nr;
-    int* ray_n = (int*)w; w += nr;
-    int* ray_idx = (int*)w; w += ns;
-    float* ts = (float*)w; w += ns;
-    float* deltas = (float*)w; w += ns;
-    float* sigmas = (float*)w; w += ns;
-    float* rgbs = (float*)w; w += 3 * ns;
-    int* counters = (int*)w;  // [0],[1] alive counts (ping-pong)  [8..11] state  [16..17] int64 total
-    int* alive_cnt = counters;
-    int* state = counters + 8;
-    int64_t* total = (int64_t*)(counters + 16);
+    const InferWs W = infer_ws(cfg, workspace);
+    int* alive_cnt = W.alive_cnt;
+    int* state = W.state;
+    int64_t* total = W.total;
 
     if (first_round == 0) {
-        NGP_CUDA(cudaMemsetAsync(counters, 0, 4096, st));
-        k_infer_init<<<ngp_div_up(n, 256), 256, 0, st>>>(*cfg, rays_o, rays_d, t_cur, t_end, opacity, depth, rgb, alive[0],
+        NGP_CUDA(cudaMemsetAsync(W.counters, 0, 4096, st));
+        NGP_COUNT_LAUNCHES(1);
+        k_infer_init<<<ngp_div_up(n, 256), 256, 0, st>>>(*cfg, rays_o, rays_d, W.t_cur, W.t_end, opacity, depth, rgb, W.alive[0],
                                                           alive_cnt);
         NGP_CHECK_LAUNCH();
     }
     for (int round = first_round; round < first_round + n_rounds; ++round) {
-        const int S = INFER_S_MAX;  // staging capacity; the round's actual quota is computed on the device
-        const int cur = round & 1, nxt = cur ^ 1;
-        const int bs = 64;
-        // the launch covers the worst case (all rays alive); blocks past the device-side count exit at once
-        const int grid = ngp_div_up(n, bs);
-        k_infer_round_begin<<<1, 1, 0, st>>>(*cfg, alive_cnt + cur, alive_cnt + nxt, state, total);
-        NGP_CHECK_LAUNCH();
-        k_infer_march<<<grid, bs, (size_t)bs * S * sizeof(float2), st>>>(
-            *cfg, S, rays_o, rays_d, density_bitfield, t_cur, t_end, alive[cur], alive_cnt + cur, ray_start, ray_n,
-            ray_idx, ts, deltas, state);
-        NGP_CHECK_LAUNCH();
-        NgpSamples smp;
-        smp.xyzs = nullptr; smp.dirs = nullptr; smp.rays_o = rays_o; smp.rays_d = rays_d; smp.ray_idx = ray_idx; smp.ts = ts;
-        smp.n = cfg->max_round_samples; smp.n_dev = state + 2; smp.live_idx = nullptr; smp.n_live_dev = nullptr;
-        int rc = ngp_net_forward(net, &smp, 1, sigmas, rgbs, nullptr, nullptr, stream);
+        int rc = infer_round(net, cfg, W, rays_o, rays_d, density_bitfield, opacity, depth, rgb, round & 1, st);
         if (rc) return rc;
-        k_infer_composite<<<grid, bs, 0, st>>>(*cfg, sigmas, rgbs, deltas, ts, ray_start, ray_n, t_cur, t_end, alive[cur],
-                                                alive_cnt + cur, opacity, depth, rgb, alive[nxt], alive_cnt + nxt);
-        NGP_CHECK_LAUNCH();
     }
     if (alive_count_out)
         NGP_CUDA(cudaMemcpyAsync(alive_count_out, alive_cnt + ((first_round + n_rounds) & 1), sizeof(int),
@@ -281,5 +285,171 @@ extern "C" int ngp_render_infer(const NgpNet* net, const NgpInferCfg* cfg, const
         k_infer_finish<<<ngp_div_up(n, 256), 256, 0, st>>>(*cfg, opacity, rgb, state, total, total_samples);
         NGP_CHECK_LAUNCH();
     }
+    return 0;
+}
+
+static int infer_round(const NgpNet* net, const NgpInferCfg* cfg, const InferWs& W, const float* rays_o, const float* rays_d,
+                       const uint8_t* density_bitfield, float* opacity, float* depth, float* rgb, int cur, cudaStream_t st) {
+    const int n = cfg->n_rays;
+    const int S = INFER_S_MAX;  // staging capacity; the round's actual quota is computed on the device
+    const int nxt = cur ^ 1;
+    const int bs = 64;
+    // the launch covers the worst case (all rays alive); blocks past the device-side count exit at once
+    const int grid = ngp_div_up(n, bs);
+    k_infer_round_begin<<<1, 1, 0, st>>>(*cfg, W.alive_cnt + cur, W.alive_cnt + nxt, W.state, W.total);
+    NGP_CHECK_LAUNCH();
+    k_infer_march<<<grid, bs, (size_t)bs * S * sizeof(float2), st>>>(
+        *cfg, S, rays_o, rays_d, density_bitfield, W.t_cur, W.t_end, W.alive[cur], W.alive_cnt + cur, W.ray_start, W.ray_n,
+        W.ray_idx, W.ts, W.deltas, W.state);
+    NGP_CHECK_LAUNCH();
+    NgpSamples smp;
+    smp.xyzs = nullptr; smp.dirs = nullptr; smp.rays_o = rays_o; smp.rays_d = rays_d; smp.ray_idx = W.ray_idx; smp.ts = W.ts;
+    smp.n = cfg->max_round_samples; smp.n_dev = W.state + 2; smp.live_idx = nullptr; smp.n_live_dev = nullptr;
+    int rc = ngp_net_forward(net, &smp, 1, W.sigmas, W.rgbs, nullptr, nullptr, (void*)st);
+    if (rc) return rc;
+    k_infer_composite<<<grid, bs, 0, st>>>(*cfg, W.sigmas, W.rgbs, W.deltas, W.ts, W.ray_start, W.ray_n, W.t_cur, W.t_end,
+                                            W.alive[cur], W.alive_cnt + cur, opacity, depth, rgb, W.alive[nxt], W.alive_cnt + nxt);
+    NGP_CHECK_LAUNCH();
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// The whole frame as ONE CUDA graph with a device-side loop: init -> WHILE(alive rays left and sample budget not used up)
+// { two rounds (the alive lists ping-pong) } -> finish. The loop is a conditional WHILE node whose condition a 1-thread
+// kernel at the end of the body sets from the device-side alive count (cudaGraphSetConditional), so the host enqueues one
+// graph launch per frame and never reads anything back. The instantiated graph is cached per (device, arguments): a
+// caller that renders frame after frame from the same buffers pays the build once.
+// -------------------------------------------------------------------------------------------------
+__global__ void k_infer_loop_cond(const NgpInferCfg cfg, const int* __restrict__ alive_count, const int* __restrict__ state,
+                                  cudaGraphConditionalHandle handle) {
+    // next iteration iff rays are left and the reference's loop condition `samples < max_samples` still holds
+    cudaGraphSetConditional(handle, (*alive_count > 0 && state[1] < cfg.sample_budget) ? 1u : 0u);
+}
+
+struct InferGraphKey {
+    NgpNet net;
+    NgpInferCfg cfg;
+    const void *rays_o, *rays_d, *bitfield, *opacity, *depth, *rgb, *total, *workspace;
+    int device;
+};
+struct InferGraphEntry {
+    InferGraphKey key;
+    cudaGraphExec_t exec;
+    cudaGraph_t graph;
+    bool used;
+};
+#define INFER_GRAPH_CACHE 8
+static InferGraphEntry g_infer_graphs[INFER_GRAPH_CACHE];
+static unsigned g_infer_graph_clock = 0;
+
+static int build_infer_graph(const InferGraphKey& k, InferGraphEntry* e) {
+    const NgpNet* net = &k.net;
+    const NgpInferCfg* cfg = &k.cfg;
+    const float* rays_o = (const float*)k.rays_o;
+    const float* rays_d = (const float*)k.rays_d;
+    const uint8_t* bitfield = (const uint8_t*)k.bitfield;
+    float* opacity = (float*)k.opacity;
+    float* depth = (float*)k.depth;
+    float* rgb = (float*)k.rgb;
+    const InferWs W = infer_ws(cfg, (void*)k.workspace);
+    const int n = cfg->n_rays;
+    cudaStream_t cs;
+    NGP_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    cudaGraph_t g = nullptr;
+    int rc = 0;
+    do {
+        if ((rc = (int)cudaGraphCreate(&g, 0))) break;
+        // ---- head: clear the counters, AABB + first alive list ----
+        if ((rc = (int)cudaStreamBeginCaptureToGraph(cs, g, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal))) break;
+        cudaMemsetAsync(W.counters, 0, 4096, cs);
+        k_infer_init<<<ngp_div_up(n, 256), 256, 0, cs>>>(*cfg, rays_o, rays_d, W.t_cur, W.t_end, opacity, depth, rgb, W.alive[0],
+                                                          W.alive_cnt);
+        cudaStreamCaptureStatus status;
+        const cudaGraphNode_t* deps = nullptr;
+        size_t n_deps = 0;
+        if ((rc = (int)cudaStreamGetCaptureInfo(cs, &status, nullptr, nullptr, &deps, &n_deps))) break;
+        cudaGraphNode_t head_tail[8];
+        if (n_deps > 8) { rc = NGP_EINVAL; break; }
+        for (size_t i = 0; i < n_deps; ++i) head_tail[i] = deps[i];
+        cudaGraph_t tmp = nullptr;
+        if ((rc = (int)cudaStreamEndCapture(cs, &tmp))) break;
+        // ---- the WHILE node ----
+        cudaGraphConditionalHandle handle;
+        if ((rc = (int)cudaGraphConditionalHandleCreate(&handle, g, 1, cudaGraphCondAssignDefault))) break;
+        cudaGraphNodeParams cp = {};
+        cp.type = cudaGraphNodeTypeConditional;
+        cp.conditional.handle = handle;
+        cp.conditional.type = cudaGraphCondTypeWhile;
+        cp.conditional.size = 1;
+        cudaGraphNode_t loop;
+        if ((rc = (int)cudaGraphAddNode(&loop, g, head_tail, n_deps, &cp))) break;
+        cudaGraph_t body = cp.conditional.phGraph_out[0];
+        if ((rc = (int)cudaStreamBeginCaptureToGraph(cs, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal))) break;
+        for (int half = 0; half < 2 && !rc; ++half)
+            rc = infer_round(net, cfg, W, rays_o, rays_d, bitfield, opacity, depth, rgb, half, cs);
+        k_infer_loop_cond<<<1, 1, 0, cs>>>(*cfg, W.alive_cnt + 0, W.state, handle);  // after two rounds list 0 is current again
+        int rc2 = (int)cudaStreamEndCapture(cs, &tmp);
+        if (rc) break;
+        if ((rc = rc2)) break;
+        // ---- tail: background + total ----
+        if ((rc = (int)cudaStreamBeginCaptureToGraph(cs, g, &loop, nullptr, 1, cudaStreamCaptureModeThreadLocal))) break;
+        k_infer_finish<<<ngp_div_up(n, 256), 256, 0, cs>>>(*cfg, opacity, rgb, W.state, W.total, (int64_t*)k.total);
+        if ((rc = (int)cudaStreamEndCapture(cs, &tmp))) break;
+        cudaGraphExec_t exec = nullptr;
+        if ((rc = (int)cudaGraphInstantiate(&exec, g, 0))) break;
+        e->exec = exec;
+        e->graph = g;
+        e->key = k;
+        e->used = true;
+        g = nullptr;
+    } while (0);
+    if (rc) {
+        // leave no capture open on the private stream
+        cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(cs, &status) == cudaSuccess && status != cudaStreamCaptureStatusNone) {
+            cudaGraph_t junk = nullptr;
+            cudaStreamEndCapture(cs, &junk);
+        }
+        cudaGetLastError();
+    }
+    if (g) cudaGraphDestroy(g);
+    cudaStreamDestroy(cs);
+    return rc;
+}
+
+extern "C" int ngp_render_infer_frame(const NgpNet* net, const NgpInferCfg* cfg, const float* rays_o, const float* rays_d,
+                                      const uint8_t* density_bitfield, float* opacity, float* depth, float* rgb,
+                                      int64_t* total_samples, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!net || !cfg || !rays_o || !rays_d || !density_bitfield || !opacity || !depth || !rgb || !workspace) return NGP_EINVAL;
+    if (cfg->n_rays < 1 || cfg->cascades < 1 || cfg->grid_size < 1 || cfg->grid_size > 1024 || cfg->max_samples < 1 ||
+        cfg->max_round_samples < cfg->n_rays || cfg->max_round_samples > 0x7fffffffll || cfg->sample_budget < 1)
+        return NGP_EINVAL;
+    if (workspace_bytes < ngp_render_infer_workspace(cfg->n_rays, cfg->max_round_samples)) return NGP_EINVAL;
+    InferGraphKey k;
+    memset(&k, 0, sizeof(k));
+    k.net = *net;
+    k.cfg = *cfg;
+    k.rays_o = rays_o; k.rays_d = rays_d; k.bitfield = density_bitfield; k.opacity = opacity; k.depth = depth; k.rgb = rgb;
+    k.total = total_samples; k.workspace = workspace;
+    NGP_CUDA(cudaGetDevice(&k.device));
+    InferGraphEntry* hit = nullptr;
+    InferGraphEntry* victim = &g_infer_graphs[g_infer_graph_clock % INFER_GRAPH_CACHE];
+    for (int i = 0; i < INFER_GRAPH_CACHE; ++i) {
+        InferGraphEntry* e = &g_infer_graphs[i];
+        if (e->used && memcmp(&e->key, &k, sizeof(k)) == 0) { hit = e; break; }
+        if (!e->used) victim = e;
+    }
+    if (!hit) {
+        if (victim->used) {
+            cudaGraphExecDestroy(victim->exec);
+            cudaGraphDestroy(victim->graph);
+            victim->used = false;
+        }
+        int rc = build_infer_graph(k, victim);
+        if (rc) return rc;
+        ++g_infer_graph_clock;
+        hit = victim;
+    }
+    NGP_CUDA(cudaGraphLaunch(hit->exec, (cudaStream_t)stream));
     return 0;
 }

@@ -182,22 +182,44 @@ __device__ __forceinline__ void to_unit(const NgpNet& net, const SampleIn& s, fl
 
 // Encode the rows this lane owns into the A fragments of the first density layer.
 // Lane (g,q) owns rows {g, g+8} of each 16-row tile and levels {q, q+4, q+8, q+12}.
-template <int MT>
+template <int MT, bool PAIRED = false, int DEPTH = 1>
 __device__ __forceinline__ void encode_rows(const NgpNet& net, const uint32_t* __restrict__ table,
                                             const float (&u)[MT][2][3], const bool (&valid)[MT][2],
                                             uint32_t (&featA)[MT][2][4], int q) {
+    if (DEPTH <= 1) {
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+            for (int h = 0; h < 2; ++h)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int level = 4 * j + q;
-                float2 f = make_float2(0.f, 0.f);
-                if (valid[mt][h] && level < net.meta.n_levels)
-                    f = grid_lookup(table, net.meta, level, u[mt][h][0], u[mt][h][1], u[mt][h][2]);
-                featA[mt][j >> 1][2 * (j & 1) + h] = pack_half2(f.x, f.y);
-            }
+                for (int j = 0; j < 4; ++j) {
+                    const int level = 4 * j + q;
+                    float2 f = make_float2(0.f, 0.f);
+                    if (valid[mt][h] && level < net.meta.n_levels)
+                        f = PAIRED ? grid_lookup_paired(table, net.meta, level, u[mt][h][0], u[mt][h][1], u[mt][h][2])
+                                   : grid_lookup(table, net.meta, level, u[mt][h][0], u[mt][h][1], u[mt][h][2]);
+                    featA[mt][j >> 1][2 * (j & 1) + h] = pack_half2(f.x, f.y);
+                }
+        return;
+    }
+    // software pipeline over the 8*MT lookups of this lane: lookup t+1 is fetched before lookup t is reduced
+    constexpr int T = 8 * MT;
+    GridFetch<PAIRED> cur, nxt;
+    auto fetch = [&](GridFetch<PAIRED>& f, int t) {
+        const int mt = t >> 3, h = (t >> 2) & 1, j = t & 3;
+        const int level = 4 * j + q;
+        grid_fetch<PAIRED>(f, table, net.meta, level < net.meta.n_levels ? level : 0, u[mt][h][0], u[mt][h][1], u[mt][h][2],
+                           valid[mt][h] && level < net.meta.n_levels);
+    };
+    fetch(cur, 0);
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        if (t + 1 < T) fetch(nxt, t + 1);
+        const float2 f = grid_reduce<PAIRED>(cur);
+        const int mt = t >> 3, h = (t >> 2) & 1, j = t & 3;
+        featA[mt][j >> 1][2 * (j & 1) + h] = pack_half2(f.x, f.y);
+        cur = nxt;
+    }
 }
 
 // SH-4 of the normalised direction, as the A fragment k-tile 0 of the rgb net input.
@@ -216,7 +238,7 @@ __device__ __forceinline__ float hi_half(uint32_t u) { return __half2float(__ush
 // -------------------------------------------------------------------------------------------------
 // forward
 // -------------------------------------------------------------------------------------------------
-template <int FWD_MT, int FWD_THREADS, int MIN_BLOCKS>
+template <int FWD_MT, int FWD_THREADS, int MIN_BLOCKS, bool PAIRED, int DEPTH>
 __global__ void __launch_bounds__(FWD_THREADS, MIN_BLOCKS)
 k_ngp_fwd(const NgpNet net, const NgpSamples smp, const int want_rgb, float* __restrict__ sigmas, float* __restrict__ rgbs,
           __half* __restrict__ h_out, uint4* __restrict__ feat_save, int* __restrict__ sched) {
@@ -253,7 +275,7 @@ k_ngp_fwd(const NgpNet net, const NgpSamples smp, const int want_rgb, float* __r
             }
 
         uint32_t featA[FWD_MT][2][4];
-        encode_rows<FWD_MT>(net, table, u, valid, featA, q);
+        encode_rows<FWD_MT, PAIRED, DEPTH>(net, table, u, valid, featA, q);
 
         if (feat_save) {
 #pragma unroll
@@ -349,8 +371,23 @@ static int launch_fwd(const NgpNet* net, const NgpSamples* smp, int want_rgb, fl
     const int64_t cap = (int64_t)ngp_sm_count() * MIN_BLOCKS;
     const int grid = (int)(want < cap ? want : cap);
     int* sched = sched_slot(st);
-    k_ngp_fwd<MT, THREADS, MIN_BLOCKS><<<grid, THREADS, 0, st>>>(*net, *smp, want_rgb, sigmas, rgbs, (__half*)h_out,
-                                                                 (uint4*)feat_save, sched);
+    // NGP_GATHER_PAIRED / NGP_GATHER_DEPTH (env, read once): aligned 8-byte x-pair loads in the hash gather; software
+    // pipelining of the lookups (hashgrid.cuh)
+    static int paired = -1, depth = -1;
+    if (paired < 0) {
+        const char* e = getenv("NGP_GATHER_PAIRED");
+        paired = e ? atoi(e) : 0;
+        e = getenv("NGP_GATHER_DEPTH");
+        depth = e ? atoi(e) : 1;
+    }
+#define NGP_LAUNCH_FWD(P, D)                                                                                              \
+    k_ngp_fwd<MT, THREADS, MIN_BLOCKS, P, D><<<grid, THREADS, 0, st>>>(*net, *smp, want_rgb, sigmas, rgbs, (__half*)h_out, \
+                                                                       (uint4*)feat_save, sched)
+    if (paired && depth > 1) NGP_LAUNCH_FWD(true, 2);
+    else if (paired) NGP_LAUNCH_FWD(true, 1);
+    else if (depth > 1) NGP_LAUNCH_FWD(false, 2);
+    else NGP_LAUNCH_FWD(false, 1);
+#undef NGP_LAUNCH_FWD
     return 0;
 }
 
@@ -980,7 +1017,7 @@ k_ngp_bwd2(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_
 #define SCATTER_THREADS 256
 __global__ void __launch_bounds__(SCATTER_THREADS)
 k_grid_scatter_merged(const NgpNet net, const NgpSamples smp, const uint32_t* __restrict__ dfeat, const int64_t dfeat_stride,
-                      const float* __restrict__ loss_scale, float* __restrict__ grad_table) {
+                      const float* __restrict__ loss_scale, float* __restrict__ grad_table, const int paired) {
     const int lane = threadIdx.x & 31;
     const int64_t n = bwd_count(smp);
     const float inv_scale = loss_scale ? 1.0f / *loss_scale : 1.0f;
@@ -995,7 +1032,12 @@ k_grid_scatter_merged(const NgpNet net, const NgpSamples smp, const uint32_t* __
         float u, v, w;
         to_unit(net, sm, u, v, w);
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        // the per-level feature gradient is the one load on the critical path of a level: fetch the NEXT level's while
+        // this level's shuffles and reductions run
+        uint32_t d_next = valid ? __ldg(dfeat + s) : 0u;
         for (int level = 0; level < n_levels; ++level) {
+            const uint32_t d_cur = d_next;
+            if (valid && level + 1 < n_levels) d_next = __ldg(dfeat + (int64_t)(level + 1) * dfeat_stride + s);
             const uint32_t res = net.meta.res[level];
             const uint32_t off = net.meta.offset[level];
             const uint32_t entries = net.meta.offset[level + 1] - off;
@@ -1003,7 +1045,7 @@ k_grid_scatter_merged(const NgpNet net, const NgpSamples smp, const uint32_t* __
             const GridCell c = grid_cell(u, v, w, net.meta.scale[level]);
             float2 gr = make_float2(0.f, 0.f);
             if (valid) {
-                gr = unpack_half2(__ldg(dfeat + (int64_t)level * dfeat_stride + s));
+                gr = unpack_half2(d_cur);
                 gr.x *= inv_scale;
                 gr.y *= inv_scale;
             }
@@ -1046,10 +1088,14 @@ k_grid_scatter_merged(const NgpNet net, const NgpSamples smp, const uint32_t* __
                 uint32_t idx[8];
                 grid_corner_indices(c, res, entries, hashed, idx);
                 const float* lvl = grad_table + 2 * (size_t)off;
+                if (paired) {
+                    grid_scatter_cell_paired(lvl, idx, acc);
+                } else {
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    red_add_f32x2(const_cast<float*>(reinterpret_cast<const float*>(entry_ptr<8>(lvl, idx[k]))), acc[2 * k],
-                                  acc[2 * k + 1]);
+                    for (int k = 0; k < 8; ++k)
+                        red_add_f32x2(const_cast<float*>(reinterpret_cast<const float*>(entry_ptr<8>(lvl, idx[k]))), acc[2 * k],
+                                      acc[2 * k + 1]);
+                }
             }
         }
     }
@@ -1124,8 +1170,14 @@ extern "C" int ngp_net_backward_scatter(const NgpNet* net, const NgpSamples* smp
     int64_t gx = (smp->n + SCATTER_THREADS - 1) / SCATTER_THREADS;
     const int64_t cap = (int64_t)ngp_sm_count() * 8;
     if (gx > cap) gx = cap;
+    // NGP_SCATTER_PAIRED (env, read once): 16-byte reductions for aligned x-corner pairs (hashgrid.cuh)
+    static int paired = -1;
+    if (paired < 0) {
+        const char* e = getenv("NGP_SCATTER_PAIRED");
+        paired = e ? atoi(e) : 0;
+    }
     k_grid_scatter_merged<<<(unsigned)gx, SCATTER_THREADS, 0, (cudaStream_t)stream>>>(
-        *net, *smp, (const uint32_t*)workspace, n_mtiles * 16, loss_scale, grad_enc + NGP_DENSITY_MLP_PARAMS);
+        *net, *smp, (const uint32_t*)workspace, n_mtiles * 16, loss_scale, grad_enc + NGP_DENSITY_MLP_PARAMS, paired);
     NGP_CHECK_LAUNCH();
     return 0;
 }

@@ -441,14 +441,7 @@ __global__ void k_march_test(const float* __restrict__ rays_o, const float* __re
             ++s;
         }
     }
-    n_eff[n] = s;
-    for (int k = s; k < n_samples_max; ++k) {
-        const int64_t q = row + k;
-        xyzs[3 * q] = 0.f; xyzs[3 * q + 1] = 0.f; xyzs[3 * q + 2] = 0.f;
-        dirs[3 * q] = 0.f; dirs[3 * q + 1] = 0.f; dirs[3 * q + 2] = 0.f;
-        ts[q] = 0.f;
-        deltas[q] = 0.f;
-    }
+    n_eff[n] = s;  // slots s.. keep the zeros of the memsets below
 }
 
 extern "C" int ngp_raymarching_test(const float* rays_o, const float* rays_d, float* hits_t, const int64_t* alive_indices,
@@ -457,6 +450,14 @@ extern "C" int ngp_raymarching_test(const float* rays_o, const float* rays_d, fl
                                     float* xyzs, float* dirs, float* deltas, float* ts, int* N_eff_samples, void* stream) {
     if (n_alive < 0 || cascades < 1 || grid_size < 1 || grid_size > 1024 || max_samples < 1 || N_samples < 1) return NGP_EINVAL;
     if (n_alive == 0) return 0;
+    // zero padding of the rectangular outputs (the reference allocates them with torch::zeros, raymarching.cu:423-426):
+    // four streaming memsets instead of strided stores from the marching threads
+    const size_t slots = (size_t)n_alive * N_samples;
+    NGP_CUDA(cudaMemsetAsync(xyzs, 0, slots * 3 * sizeof(float), (cudaStream_t)stream));
+    NGP_CUDA(cudaMemsetAsync(dirs, 0, slots * 3 * sizeof(float), (cudaStream_t)stream));
+    NGP_CUDA(cudaMemsetAsync(deltas, 0, slots * sizeof(float), (cudaStream_t)stream));
+    NGP_CUDA(cudaMemsetAsync(ts, 0, slots * sizeof(float), (cudaStream_t)stream));
+    NGP_COUNT_LAUNCHES(4);
     const int bs = n_alive >= 148 * 128 * 4 ? 128 : 64;
     k_march_test<<<ngp_div_up(n_alive, bs), bs, 0, (cudaStream_t)stream>>>(
         rays_o, rays_d, hits_t, alive_indices, density_bitfield, cascades, grid_size, scale, exp_step_factor, N_samples,

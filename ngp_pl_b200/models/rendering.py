@@ -54,14 +54,13 @@ def _background(exp_step_factor, device, random_bg=False):
 
 @torch.no_grad()
 def _render_rays_test_fused(model, rays_o, rays_d, hits_t, **kwargs):
-    """Inference through ngp_render_infer: a device-side wavefront; the host only reads the number of
-    alive rays back once every `rounds_per_check` rounds (the reference synchronises >= 3 times per round)."""
+    """Inference as a device-side wavefront. Default: ngp_render_infer_frame -- the whole frame is ONE CUDA graph with a
+    device-side while loop, no host read-back (graph=False or a driver without conditional graph nodes: ngp_render_infer,
+    `rounds_per_check` rounds per host read of the alive count; the reference synchronises >= 3 times per round)."""
     from .networks import _net_struct
     exp_step_factor = kwargs.get('exp_step_factor', 0.)
     N = rays_o.shape[0]
     dev = rays_o.device
-    rays_o = rays_o.float().contiguous()
-    rays_d = rays_d.float().contiguous()
     with torch.cuda.device(dev):
         L = _lib.lib()
         cfg = _lib.NgpInferCfg()
@@ -75,39 +74,54 @@ def _render_rays_test_fused(model, rays_o, rays_d, hits_t, **kwargs):
         cfg.sample_budget = int(kwargs.get('max_samples', MAX_SAMPLES))
         cfg.max_round_samples = max(4 * N, 1 << 16)
         ws_bytes = L.ngp_render_infer_workspace(N, cfg.max_round_samples)
-        cache = getattr(model, '_infer_ws', None)
-        if cache is None or cache.numel() < ws_bytes or cache.device != dev:
-            cache = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
-            model._infer_ws = cache
+        # persistent per-model buffers: workspace, staged rays and outputs keep their addresses from frame to frame, which
+        # is what lets the cached frame graph be replayed
+        cache = getattr(model, '_infer_cache', None)
+        if cache is None or cache['N'] != N or cache['dev'] != dev or cache['ws'].numel() < ws_bytes:
+            cache = dict(N=N, dev=dev, ws=torch.empty(ws_bytes, device=dev, dtype=torch.uint8),
+                         o=torch.empty(N, 3, device=dev), d=torch.empty(N, 3, device=dev), opacity=torch.empty(N, device=dev),
+                         depth=torch.empty(N, device=dev), rgb=torch.empty(N, 3, device=dev),
+                         total=torch.zeros(1, device=dev, dtype=torch.int64), alive=torch.zeros(1, device=dev, dtype=torch.int32),
+                         alive_host=torch.zeros(1, dtype=torch.int32).pin_memory())
+            model._infer_cache = cache
+        ws, o, d = cache['ws'], cache['o'], cache['d']
+        opacity, depth, rgb, total = cache['opacity'], cache['depth'], cache['rgb'], cache['total']
+        o.copy_(rays_o)
+        d.copy_(rays_d)
         net, keep = _net_struct(model)
-        opacity = torch.empty(N, device=dev)
-        depth = torch.empty(N, device=dev)
-        rgb = torch.empty(N, 3, device=dev)
-        total = torch.zeros(1, device=dev, dtype=torch.int64)
-        alive = torch.zeros(1, device=dev, dtype=torch.int32)
-        alive_host = getattr(model, '_infer_alive_host', None)
-        if alive_host is None:
-            alive_host = torch.zeros(1, dtype=torch.int32).pin_memory()
-            model._infer_alive_host = alive_host
         st = torch.cuda.current_stream().cuda_stream
-        chunk = int(kwargs.get('rounds_per_check', 8))
-        first = 0
-        while True:
-            # `chunk` rounds are enqueued back to back; the alive count is read back once per chunk
-            rc = L.ngp_render_infer(C.byref(net), C.byref(cfg), rays_o.data_ptr(), rays_d.data_ptr(),
-                                    model.density_bitfield.data_ptr(), opacity.data_ptr(), depth.data_ptr(), rgb.data_ptr(),
-                                    total.data_ptr(), first, chunk, 0, alive.data_ptr(), cache.data_ptr(), cache.numel(), st)
-            _lib.check(rc, "render_infer")
-            first += chunk
-            alive_host.copy_(alive, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            if int(alive_host[0]) == 0 or first > 2 * cfg.sample_budget:
-                break
-        rc = L.ngp_render_infer(C.byref(net), C.byref(cfg), rays_o.data_ptr(), rays_d.data_ptr(),
-                                model.density_bitfield.data_ptr(), opacity.data_ptr(), depth.data_ptr(), rgb.data_ptr(),
-                                total.data_ptr(), first, 0, 1, None, cache.data_ptr(), cache.numel(), st)
-        _lib.check(rc, "render_infer(finish)")
-    return {'opacity': opacity, 'depth': depth, 'rgb': rgb, 'total_samples': total[0]}
+        done = False
+        if kwargs.get('graph', True) and getattr(model, '_infer_graph_ok', True):
+            rc = L.ngp_render_infer_frame(C.byref(net), C.byref(cfg), o.data_ptr(), d.data_ptr(), model.density_bitfield.data_ptr(),
+                                          opacity.data_ptr(), depth.data_ptr(), rgb.data_ptr(), total.data_ptr(), ws.data_ptr(),
+                                          ws.numel(), st)
+            if rc == 0:
+                done = True
+            elif rc < 0:
+                _lib.check(rc, "render_infer_frame")
+            else:
+                model._infer_graph_ok = False  # conditional graph nodes unavailable: host-chunked rounds from now on
+        if not done:
+            alive, alive_host = cache['alive'], cache['alive_host']
+            chunk = int(kwargs.get('rounds_per_check', 8))
+            first = 0
+            while True:
+                # `chunk` rounds are enqueued back to back; the alive count is read back once per chunk
+                rc = L.ngp_render_infer(C.byref(net), C.byref(cfg), o.data_ptr(), d.data_ptr(), model.density_bitfield.data_ptr(),
+                                        opacity.data_ptr(), depth.data_ptr(), rgb.data_ptr(), total.data_ptr(), first, chunk, 0,
+                                        alive.data_ptr(), ws.data_ptr(), ws.numel(), st)
+                _lib.check(rc, "render_infer")
+                first += chunk
+                alive_host.copy_(alive, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                if int(alive_host[0]) == 0 or first > 2 * cfg.sample_budget:
+                    break
+            rc = L.ngp_render_infer(C.byref(net), C.byref(cfg), o.data_ptr(), d.data_ptr(), model.density_bitfield.data_ptr(),
+                                    opacity.data_ptr(), depth.data_ptr(), rgb.data_ptr(), total.data_ptr(), first, 0, 1, None,
+                                    ws.data_ptr(), ws.numel(), st)
+            _lib.check(rc, "render_infer(finish)")
+        # fresh tensors for the caller (the persistent ones are overwritten by the next frame)
+        return {'opacity': opacity.clone(), 'depth': depth.clone(), 'rgb': rgb.clone(), 'total_samples': total[0].clone()}
 
 
 @torch.no_grad()

@@ -24,6 +24,24 @@ def _st():
     return torch.cuda.current_stream().cuda_stream
 
 
+class _Same:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_SAME = _Same()
+
+
+def _on(dev):
+    """device guard that costs nothing when `dev` already is the current device (the reference has none at all)"""
+    if dev.index is None or dev.index == torch.cuda.current_device():
+        return _SAME
+    return torch.cuda.device(dev)
+
+
 def _p(t):
     return t.data_ptr()
 
@@ -38,7 +56,7 @@ def _intersect(fn_name, rays_o, rays_d, centers, extents, max_hits):
     _chk(rays_o, rays_d, centers, extents)
     n_rays, n_obj = rays_o.shape[0], centers.shape[0]
     dev = rays_o.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         hits_t = torch.empty(n_rays, max_hits, 2, device=dev, dtype=torch.float32)
         hits_idx = torch.empty(n_rays, max_hits, device=dev, dtype=torch.int64)
         hit_cnt = torch.empty(n_rays, device=dev, dtype=torch.int32)
@@ -71,7 +89,7 @@ def packbits(density_grid, density_threshold, density_bitfield):
     _chk(density_grid, density_bitfield)
     if density_grid.dtype not in _DTYPE_CODE:
         raise RuntimeError("packbits: unsupported dtype %s" % density_grid.dtype)
-    with torch.cuda.device(density_grid.device):
+    with _on(density_grid.device):
         rc = _lib.lib().ngp_packbits(_p(density_grid), _DTYPE_CODE[density_grid.dtype], density_bitfield.shape[0],
                                      float(density_threshold), None, _p(density_bitfield), _st())
     _lib.check(rc, "packbits")
@@ -83,7 +101,7 @@ def morton3D(coords):
     if coords.dtype != torch.int32:
         raise RuntimeError("morton3D: expected int32 coords")
     out = torch.empty(coords.shape[0], device=coords.device, dtype=torch.int32)
-    with torch.cuda.device(coords.device):
+    with _on(coords.device):
         _lib.check(_lib.lib().ngp_morton3D(_p(coords), coords.shape[0], _p(out), _st()), "morton3D")
     return out
 
@@ -94,7 +112,7 @@ def morton3D_invert(indices):
     if indices.dtype != torch.int32:
         raise RuntimeError("morton3D_invert: expected int32 indices")
     out = torch.empty(indices.shape[0], 3, device=indices.device, dtype=torch.int32)
-    with torch.cuda.device(indices.device):
+    with _on(indices.device):
         _lib.check(_lib.lib().ngp_morton3D_invert(_p(indices), indices.shape[0], _p(out), _st()), "morton3D_invert")
     return out
 
@@ -107,7 +125,7 @@ def raymarching_train(rays_o, rays_d, hits_t, density_bitfield, cascades, scale,
     n_rays = rays_o.shape[0]
     dev = rays_o.device
     cap = n_rays * int(max_samples)
-    with torch.cuda.device(dev):
+    with _on(dev):
         rays_a = torch.empty(n_rays, 3, device=dev, dtype=torch.int64)
         xyzs = torch.empty(cap, 3, device=dev, dtype=torch.float32)
         dirs = torch.empty(cap, 3, device=dev, dtype=torch.float32)
@@ -134,7 +152,7 @@ def raymarching_test(rays_o, rays_d, hits_t, alive_indices, density_bitfield, ca
         raise RuntimeError("raymarching_test: alive_indices must be int64")
     n_alive = alive_indices.shape[0]
     dev = rays_o.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         xyzs = torch.empty(n_alive, N_samples, 3, device=dev, dtype=torch.float32)
         dirs = torch.empty(n_alive, N_samples, 3, device=dev, dtype=torch.float32)
         deltas = torch.empty(n_alive, N_samples, device=dev, dtype=torch.float32)
@@ -153,7 +171,7 @@ def composite_train_fw(sigmas, rgbs, deltas, ts, rays_a, T_threshold):
     _chk(sigmas, rgbs, deltas, ts, rays_a)
     n_rays, n = rays_a.shape[0], sigmas.shape[0]
     dev = sigmas.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         total = torch.empty(n_rays, device=dev, dtype=torch.int64)
         opacity = torch.empty(n_rays, device=dev, dtype=torch.float32)
         depth = torch.empty(n_rays, device=dev, dtype=torch.float32)
@@ -172,7 +190,7 @@ def composite_train_bw(dL_dopacity, dL_ddepth, dL_drgb, dL_dws, sigmas, rgbs, ws
     _chk(dL_dopacity, dL_ddepth, dL_drgb, dL_dws, sigmas, rgbs, ws, deltas, ts, rays_a, opacity, depth, rgb)
     n_rays, n = rays_a.shape[0], sigmas.shape[0]
     dev = sigmas.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         dsig = torch.empty(n, device=dev, dtype=torch.float32)
         drgbs = torch.empty(n, 3, device=dev, dtype=torch.float32)
         rc = _lib.lib().ngp_composite_train_bw(
@@ -189,7 +207,7 @@ def composite_test_fw(sigmas, rgbs, deltas, ts, hits_t, alive_indices, T_thresho
     _chk(sigmas, rgbs, deltas, ts, hits_t, alive_indices, N_eff_samples, opacity, depth, rgb)
     n_alive = alive_indices.shape[0]
     n_samples = sigmas.shape[1] if sigmas.dim() == 2 else 1
-    with torch.cuda.device(sigmas.device):
+    with _on(sigmas.device):
         rc = _lib.lib().ngp_composite_test_fw(_p(_f32(sigmas)), _p(_f32(rgbs)), _p(_f32(deltas)), _p(_f32(ts)),
                                               _p(hits_t), _p(alive_indices), float(T_threshold), _p(N_eff_samples),
                                               n_alive, n_samples, _p(_f32(opacity)), _p(_f32(depth)), _p(_f32(rgb)),
@@ -202,7 +220,7 @@ def distortion_loss_fw(ws, deltas, ts, rays_a):
     _chk(ws, deltas, ts, rays_a)
     n_rays, n = rays_a.shape[0], ws.shape[0]
     dev = ws.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         loss = torch.zeros(n_rays, device=dev, dtype=torch.float32)
         ws_inc = torch.empty(n, device=dev, dtype=torch.float32)
         wts_inc = torch.empty(n, device=dev, dtype=torch.float32)
@@ -217,7 +235,7 @@ def distortion_loss_bw(dL_dloss, ws_inclusive_scan, wts_inclusive_scan, ws, delt
     _chk(dL_dloss, ws_inclusive_scan, wts_inclusive_scan, ws, deltas, ts, rays_a)
     n_rays, n = rays_a.shape[0], ws.shape[0]
     dev = ws.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         dws = torch.zeros(n, device=dev, dtype=torch.float32)
         rc = _lib.lib().ngp_distortion_loss_bw(_p(_f32(dL_dloss)), _p(_f32(ws_inclusive_scan)),
                                                _p(_f32(wts_inclusive_scan)), _p(_f32(ws)), _p(_f32(deltas)),
