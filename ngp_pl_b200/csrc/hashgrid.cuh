@@ -117,120 +117,10 @@ __device__ __forceinline__ float2 grid_lookup(const uint32_t* __restrict__ table
 
 // The two x-corners of a cell (k, k+1) sit in ONE aligned entry pair whenever their indices differ only in bit 0: for a
 // hashed level whenever gx is even ((x ^ t) and ((x+1) ^ t)), for a dense level whenever the first index is even (and the
-// pair does not straddle the wrap). The paired variants exploit that:
-//   gather : the load of corner k always fetches its aligned 8-byte pair (same sector as the 4-byte load, no extra
-//            traffic); corner k+1 is taken from it when paired and loaded by a PREDICATED 4-byte load otherwise, so the
-//            second request of every pair carries about half the lanes and half the L1 wavefronts;
-//   scatter: one 16-byte red.global.add.v4.f32 instead of two 8-byte ones when paired (one L2 atomic transaction).
-// Same values, same summation order per entry as the unpaired code.
-__device__ __forceinline__ float2 grid_lookup_paired(const uint32_t* __restrict__ table, const NgpGridMeta& m, int level, float x01,
-                                                     float y01, float z01) {
-    const uint32_t res = m.res[level];
-    const uint32_t off = m.offset[level];
-    const uint32_t entries = m.offset[level + 1] - off;
-    const bool hashed = (m.hashed_mask >> level) & 1u;
-    const GridCell c = grid_cell(x01, y01, z01, m.scale[level]);
-    uint32_t idx[8], v[8];
-    grid_corner_indices(c, res, entries, hashed, idx);
-    const uint32_t* lvl = table + off;
-    uint2 pr[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) pr[j] = __ldg(reinterpret_cast<const uint2*>(entry_ptr<4>(lvl, idx[2 * j] & ~1u)));
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const bool paired = (idx[2 * j] ^ idx[2 * j + 1]) == 1u;
-        uint32_t other = 0u;
-        if (!paired) other = __ldg(reinterpret_cast<const uint32_t*>(entry_ptr<4>(lvl, idx[2 * j + 1])));
-        const bool odd = idx[2 * j] & 1u;
-        v[2 * j] = odd ? pr[j].y : pr[j].x;
-        v[2 * j + 1] = paired ? (odd ? pr[j].x : pr[j].y) : other;
-    }
-    float w[8];
-    grid_corner_weights(c, w);
-    float f0 = 0.f, f1 = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const float2 t = unpack_half2(v[k]);
-        f0 = fmaf(w[k], t.x, f0);
-        f1 = fmaf(w[k], t.y, f1);
-    }
-    return make_float2(f0, f1);
-}
-
-// Split lookup for software pipelining: grid_fetch() computes the corner addresses of one (sample, level) and ISSUES its
-// loads, grid_reduce() consumes them. A caller that fetches lookup i+1 before reducing lookup i keeps twice the loads in
-// flight per warp (the gather is latency-bound: ~190 dependent instructions sit between two batches of 8 loads otherwise).
-template <bool PAIRED>
-struct GridFetch {
-    uint32_t a[8];               // unpaired: the 8 corner words; paired: the aligned pair of corner 2j in a[2j], a[2j+1]
-    uint32_t b[PAIRED ? 4 : 1];  // paired: corner 2j+1 when it is NOT in that pair
-    uint32_t flags;              // paired: bit j = pair j aligned, bit 4+j = index of corner 2j odd
-    float wx, wy, wz;
-};
-template <bool PAIRED>
-__device__ __forceinline__ void grid_fetch(GridFetch<PAIRED>& f, const uint32_t* __restrict__ table, const NgpGridMeta& m, int level,
-                                           float x01, float y01, float z01, bool active) {
-    f.flags = 0u;
-    f.wx = f.wy = f.wz = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) f.a[k] = 0u;
-#pragma unroll
-    for (int k = 0; k < (PAIRED ? 4 : 1); ++k) f.b[k] = 0u;
-    if (!active) return;
-    const uint32_t res = m.res[level];
-    const uint32_t off = m.offset[level];
-    const uint32_t entries = m.offset[level + 1] - off;
-    const bool hashed = (m.hashed_mask >> level) & 1u;
-    const GridCell c = grid_cell(x01, y01, z01, m.scale[level]);
-    f.wx = c.wx; f.wy = c.wy; f.wz = c.wz;
-    uint32_t idx[8];
-    grid_corner_indices(c, res, entries, hashed, idx);
-    const uint32_t* lvl = table + off;
-    if (PAIRED) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint2 pr = __ldg(reinterpret_cast<const uint2*>(entry_ptr<4>(lvl, idx[2 * j] & ~1u)));
-            f.a[2 * j] = pr.x;
-            f.a[2 * j + 1] = pr.y;
-            const bool paired = (idx[2 * j] ^ idx[2 * j + 1]) == 1u;
-            if (!paired) f.b[j] = __ldg(reinterpret_cast<const uint32_t*>(entry_ptr<4>(lvl, idx[2 * j + 1])));
-            f.flags |= (paired ? 1u : 0u) << j;
-            f.flags |= (idx[2 * j] & 1u) << (4 + j);
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) f.a[k] = __ldg(reinterpret_cast<const uint32_t*>(entry_ptr<4>(lvl, idx[k])));
-    }
-}
-template <bool PAIRED>
-__device__ __forceinline__ float2 grid_reduce(const GridFetch<PAIRED>& f) {
-    uint32_t v[8];
-    if (PAIRED) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const bool paired = (f.flags >> j) & 1u, odd = (f.flags >> (4 + j)) & 1u;
-            v[2 * j] = odd ? f.a[2 * j + 1] : f.a[2 * j];
-            v[2 * j + 1] = paired ? (odd ? f.a[2 * j] : f.a[2 * j + 1]) : f.b[j];
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = f.a[k];
-    }
-    GridCell c;
-    c.gx = c.gy = c.gz = 0u;
-    c.wx = f.wx; c.wy = f.wy; c.wz = f.wz;
-    float w[8];
-    grid_corner_weights(c, w);
-    float f0 = 0.f, f1 = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const float2 t = unpack_half2(v[k]);
-        f0 = fmaf(w[k], t.x, f0);
-        f1 = fmaf(w[k], t.y, f1);
-    }
-    return make_float2(f0, f1);
-}
-
+// pair does not straddle the wrap). The scatter uses that: one 16-byte red.global.add.v4.f32 instead of two 8-byte ones
+// (one L2 atomic transaction; measured -1.5 % on the kernel warm, -5 % cold). The same trick in the GATHER (aligned 8-byte
+// pair load + predicated load of the unpaired corner) and a software-pipelined gather were measured SLOWER than the plain
+// eight 4-byte loads (80.6 / 79.7 vs 77.6 us; profiles/r02_variant_sweep.txt) and are not kept.
 // the 8 corner contributions acc[2k], acc[2k+1] of one cell into the gradient table of a level, x-pairs merged when aligned
 __device__ __forceinline__ void grid_scatter_cell_paired(const float* lvl /* level base, float2 per entry */, const uint32_t (&idx)[8],
                                                          const float (&acc)[16]) {

@@ -52,10 +52,19 @@ __global__ void k_infer_init(const NgpInferCfg cfg, const float* __restrict__ ra
 //       N_samples = max(min(N_rays // N_alive, 64), min_samples);  samples += N_samples
 // computed from the device-side alive count. N_alive * N_samples <= max(N_rays, min_samples * N_alive) <= 4 * N_rays, the
 // capacity of the per-round sample buffers (max_round_samples), so the quota never has to be clipped.
-// state: [0] N_samples of this round (0 = loop over)  [1] `samples` so far  [2] sample count of this round  [3] rounds run
+// Two marching regimes (both kernels are launched every round, the one whose regime it is not exits at once):
+//   N_samples <  INFER_WARP_MIN : many rays, few samples each -> one THREAD per ray, samples staged in shared memory and
+//                                 appended compactly (one atomic per warp);
+//   N_samples >= INFER_WARP_MIN : few rays (<= N_rays / 8), many samples each -> one WARP per ray (march_ray_warp, 32 chain
+//                                 points probed side by side), samples written straight to the ray's own N_samples slots,
+//                                 unused slots marked ray_idx = -1 (the network kernel skips their gathers).
+// state: [0] N_samples of this round (0 = loop over)  [1] `samples` so far  [2] slots the network evaluates this round
+//        [3] rounds run  [4] samples marched this round
+#define INFER_WARP_MIN 8
 __global__ void k_infer_round_begin(const NgpInferCfg cfg, int* __restrict__ alive_count, int* __restrict__ next_count,
                                     int* __restrict__ state, int64_t* __restrict__ total) {
-    *total += state[2];
+    *total += state[4];
+    state[4] = 0;
     state[2] = 0;
     *next_count = 0;
     int n_alive = *alive_count;
@@ -71,65 +80,115 @@ __global__ void k_infer_round_begin(const NgpInferCfg cfg, int* __restrict__ ali
         if (share < S) S = (int)(share < 1 ? 1 : share);
         state[1] += S;
         state[3] += 1;
+        if (S >= INFER_WARP_MIN) state[2] = n_alive * S;  // rectangular slots; the thread-per-ray regime counts as it appends
     }
     state[0] = S;
 }
 
-// one round of marching: every alive ray takes up to S occupied samples (staged in shared memory),
-// then the warp claims a contiguous range of the compact sample arrays with one atomic.
-__global__ void k_infer_march(const NgpInferCfg cfg, const int S_max, const float* __restrict__ rays_o,
-                              const float* __restrict__ rays_d, const uint8_t* __restrict__ bitfield,
-                              float* __restrict__ t_cur, const float* __restrict__ t_end, const int* __restrict__ alive,
-                              const int* __restrict__ alive_count, int* __restrict__ ray_start, int* __restrict__ ray_n,
-                              int* __restrict__ ray_idx, float* __restrict__ ts, float* __restrict__ deltas,
-                              int* __restrict__ state) {
-    extern __shared__ float2 stage[];  // [blockDim.x][S_max]
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// one round of marching, thread-per-ray regime: every alive ray takes up to S < INFER_WARP_MIN occupied samples (staged in
+// shared memory), then the warp claims a contiguous range of the compact sample arrays with one atomic.
+#define INFER_A_THREADS 128
+__global__ void __launch_bounds__(INFER_A_THREADS)
+k_infer_march(const NgpInferCfg cfg, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+              const uint8_t* __restrict__ bitfield, float* __restrict__ t_cur, const float* __restrict__ t_end,
+              const int* __restrict__ alive, const int* __restrict__ alive_count, int* __restrict__ ray_start,
+              int* __restrict__ ray_n, int* __restrict__ ray_idx, float* __restrict__ ts, float* __restrict__ deltas,
+              int* __restrict__ state) {
+    __shared__ float2 stage[INFER_A_THREADS][INFER_WARP_MIN];
+    const int S = state[0];
+    if (S <= 0 || S >= INFER_WARP_MIN) return;
     const int lane = threadIdx.x & 31;
     const int n_alive = *alive_count;
-    if ((int)(blockIdx.x * blockDim.x) >= n_alive) return;
-    const int S = min(state[0], S_max);
-    float2* my = stage + (size_t)threadIdx.x * S_max;
-    int n = 0, r = -1;
-    float t = 0.f;
-    if (i < n_alive) {
-        r = alive[i];
-        const MarchConst c = make_march_const(bitfield, cfg.cascades, cfg.grid_size, cfg.max_samples, cfg.scale,
-                                              cfg.exp_step_factor, (float)cfg.cascades);
-        const MarchRay ray = make_march_ray(rays_o[3 * r], rays_o[3 * r + 1], rays_o[3 * r + 2],
-                                            rays_d[3 * r], rays_d[3 * r + 1], rays_d[3 * r + 2]);
-        t = t_cur[r];
-        const float t2 = t_end[r];
-        float x, y, z, dt;
-        while (t < t2 && n < S) {
-            if (march_visit(ray, c, t, x, y, z, dt)) {
-                my[n] = make_float2(t, dt);
-                t = __fadd_rn(t, dt);
-                ++n;
+    const MarchConst c = make_march_const(bitfield, cfg.cascades, cfg.grid_size, cfg.max_samples, cfg.scale, cfg.exp_step_factor,
+                                          (float)cfg.cascades);
+    // whole warps stride over the alive list (a warp's 32 rays append with one atomic)
+    const int n_pad = (n_alive + 31) & ~31;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) {
+        float2* my = stage[threadIdx.x];
+        int n = 0, r = -1;
+        float t = 0.f;
+        if (i < n_alive) {
+            r = alive[i];
+            const MarchRay ray = make_march_ray(rays_o[3 * r], rays_o[3 * r + 1], rays_o[3 * r + 2],
+                                                rays_d[3 * r], rays_d[3 * r + 1], rays_d[3 * r + 2]);
+            t = t_cur[r];
+            const float t2 = t_end[r];
+            float x, y, z, dt;
+            while (t < t2 && n < S) {
+                if (march_visit(ray, c, t, x, y, z, dt)) {
+                    my[n] = make_float2(t, dt);
+                    t = __fadd_rn(t, dt);
+                    ++n;
+                }
             }
         }
-    }
-    // inclusive prefix of the counts across the warp, one atomic per warp
-    int pre = n;
+        // inclusive prefix of the counts across the warp, one atomic per warp
+        int pre = n;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int u = __shfl_up_sync(0xffffffffu, pre, o);
-        if (lane >= o) pre += u;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, pre, o);
+            if (lane >= o) pre += u;
+        }
+        const int warp_total = __shfl_sync(0xffffffffu, pre, 31);
+        int base = 0;
+        if (lane == 31 && warp_total > 0) {
+            base = atomicAdd(&state[2], warp_total);
+            atomicAdd(&state[4], warp_total);
+        }
+        base = __shfl_sync(0xffffffffu, base, 31);
+        if (r < 0) continue;
+        const int start = base + pre - n;  // n_alive * S <= capacity, so this always fits
+        ray_start[i] = start;
+        ray_n[i] = n;
+        t_cur[r] = t;
+        for (int k = 0; k < n; ++k) {
+            ray_idx[start + k] = r;
+            ts[start + k] = my[k].x;
+            deltas[start + k] = my[k].y;
+        }
     }
-    const int warp_total = __shfl_sync(0xffffffffu, pre, 31);
-    int base = 0;
-    if (lane == 31 && warp_total > 0) base = atomicAdd(&state[2], warp_total);
-    base = __shfl_sync(0xffffffffu, base, 31);
-    if (r < 0) return;
-    const int start = base + pre - n;  // n_alive * S <= capacity, so this always fits
-    ray_start[i] = start;
-    ray_n[i] = n;
-    t_cur[r] = t;
-    for (int k = 0; k < n; ++k) {
-        ray_idx[start + k] = r;
-        ts[start + k] = my[k].x;
-        deltas[start + k] = my[k].y;
+}
+
+// warp-per-ray regime (S >= INFER_WARP_MIN): same sample sequence, 32 chain points probed at a time (march_ray_warp);
+// ray i owns slots [i*S, (i+1)*S)
+template <bool CONST_DT, bool ONE_CASCADE>
+__global__ void __launch_bounds__(128)
+k_infer_march_warp(const NgpInferCfg cfg, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                   const uint8_t* __restrict__ bitfield, float* __restrict__ t_cur, const float* __restrict__ t_end,
+                   const int* __restrict__ alive, const int* __restrict__ alive_count, int* __restrict__ ray_start,
+                   int* __restrict__ ray_n, int* __restrict__ ray_idx, float* __restrict__ ts, float* __restrict__ deltas,
+                   int* __restrict__ state) {
+    const int S = state[0];
+    if (S < INFER_WARP_MIN) return;
+    const int lane = threadIdx.x & 31;
+    const int n_alive = *alive_count;
+    const MarchConst c = make_march_const(bitfield, cfg.cascades, cfg.grid_size, cfg.max_samples, cfg.scale, cfg.exp_step_factor,
+                                          (float)cfg.cascades);
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    int marched = 0;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_alive; i += n_warps) {
+        const int r = alive[i];
+        const MarchRay ray = make_march_ray(rays_o[3 * r], rays_o[3 * r + 1], rays_o[3 * r + 2],
+                                            rays_d[3 * r], rays_d[3 * r + 1], rays_d[3 * r + 2]);
+        const float t = t_cur[r];
+        const float t2 = t_end[r];
+        const int64_t base = (int64_t)i * S;
+        float resume = t;
+        const int n = march_ray_warp<CONST_DT, ONE_CASCADE>(ray, c, t, t2, S, lane, [&](int k, float tk, float dk) {
+            ray_idx[base + k] = r;
+            ts[base + k] = tk;
+            deltas[base + k] = dk;
+        }, &resume);
+        for (int k = n + lane; k < S; k += 32) ray_idx[base + k] = -1;  // unused slots
+        if (lane == 0) {
+            ray_start[i] = (int)base;
+            ray_n[i] = n;
+            // a ray that took fewer than S samples has left the box: nothing more to march (the reference keeps its t there too)
+            t_cur[r] = n < S ? fmaxf(resume, t2) : resume;
+            marched += n;
+        }
     }
+    if (lane == 0 && marched) atomicAdd(&state[4], marched);
 }
 
 // composite this round's samples of every alive ray (one thread per ray, <= 64 samples, same serial
@@ -142,57 +201,58 @@ __global__ void k_infer_composite(const NgpInferCfg cfg, const float* __restrict
                                   const int* __restrict__ alive_count, float* __restrict__ opacity,
                                   float* __restrict__ depth, float* __restrict__ rgb, int* __restrict__ next_alive,
                                   int* __restrict__ next_count) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int n_alive = *alive_count;
-    if ((int)(blockIdx.x * blockDim.x) >= n_alive) return;
-    bool keep = false;
-    int r = -1;
-    if (i < n_alive) {
-        r = alive[i];
-        const int n = ray_n[i];
-        const int start = ray_start[i];
-        float o = opacity[r], d = depth[r];
-        float cr = rgb[3 * r], cg = rgb[3 * r + 1], cb = rgb[3 * r + 2];
-        float T = 1.0f - o;
-        bool term = false;
-        for (int s = 0; s < n; ++s) {
-            const int k = start + s;
-            const float a = 1.0f - __expf(-(__ldg(sigmas + k) * __ldg(deltas + k)));
-            const float w = a * T;
-            cr = fmaf(w, __ldg(rgbs + 3 * k), cr);
-            cg = fmaf(w, __ldg(rgbs + 3 * k + 1), cg);
-            cb = fmaf(w, __ldg(rgbs + 3 * k + 2), cb);
-            d = fmaf(w, __ldg(ts + k), d);
-            o += w;
-            T *= 1.0f - a;
-            if (T <= cfg.T_threshold) {
-                term = true;
-                break;
+    const int n_pad = (n_alive + 31) & ~31;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) {
+        bool keep = false;
+        int r = -1;
+        if (i < n_alive) {
+            r = alive[i];
+            const int n = ray_n[i];
+            const int start = ray_start[i];
+            float o = opacity[r], d = depth[r];
+            float cr = rgb[3 * r], cg = rgb[3 * r + 1], cb = rgb[3 * r + 2];
+            float T = 1.0f - o;
+            bool term = false;
+            for (int s = 0; s < n; ++s) {
+                const int k = start + s;
+                const float a = 1.0f - __expf(-(__ldg(sigmas + k) * __ldg(deltas + k)));
+                const float w = a * T;
+                cr = fmaf(w, __ldg(rgbs + 3 * k), cr);
+                cg = fmaf(w, __ldg(rgbs + 3 * k + 1), cg);
+                cb = fmaf(w, __ldg(rgbs + 3 * k + 2), cb);
+                d = fmaf(w, __ldg(ts + k), d);
+                o += w;
+                T *= 1.0f - a;
+                if (T <= cfg.T_threshold) {
+                    term = true;
+                    break;
+                }
             }
+            opacity[r] = o;
+            depth[r] = d;
+            rgb[3 * r] = cr; rgb[3 * r + 1] = cg; rgb[3 * r + 2] = cb;
+            // the reference's rule (composite_test_fw, volumerendering.cu:221-224,:245-248): a ray leaves the alive list when it
+            // got no sample this round or its transmittance fell to the threshold -- a ray that ran out of box with SOME samples
+            // stays for one more (empty) round, and counts in that round's N_alive
+            keep = !term && n > 0;
         }
-        opacity[r] = o;
-        depth[r] = d;
-        rgb[3 * r] = cr; rgb[3 * r + 1] = cg; rgb[3 * r + 2] = cb;
-        // the reference's rule (composite_test_fw, volumerendering.cu:221-224,:245-248): a ray leaves the alive list when it
-        // got no sample this round or its transmittance fell to the threshold -- a ray that ran out of box with SOME samples
-        // stays for one more (empty) round, and counts in that round's N_alive
-        keep = !term && n > 0;
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, keep);
-    if (m) {
-        int base = 0;
-        const int leader = __ffs(m) - 1;
-        if (lane == leader) base = atomicAdd(next_count, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (keep) next_alive[base + __popc(m & ((1u << lane) - 1u))] = r;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (m) {
+            int base = 0;
+            const int leader = __ffs(m) - 1;
+            if (lane == leader) base = atomicAdd(next_count, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (keep) next_alive[base + __popc(m & ((1u << lane) - 1u))] = r;
+        }
     }
 }
 
 __global__ void k_infer_finish(const NgpInferCfg cfg, const float* __restrict__ opacity, float* __restrict__ rgb,
                                const int* __restrict__ state, int64_t* __restrict__ total, int64_t* __restrict__ total_out) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r == 0 && total_out) *total_out = *total + state[2];
+    if (r == 0 && total_out) *total_out = *total + state[4];
     if (r >= cfg.n_rays) return;
     const float rest = 1.0f - opacity[r];  // reference rendering.py:112-116
     rgb[3 * r] += cfg.bg[0] * rest;
@@ -200,7 +260,6 @@ __global__ void k_infer_finish(const NgpInferCfg cfg, const float* __restrict__ 
     rgb[3 * r + 2] += cfg.bg[2] * rest;
 }
 
-#define INFER_S_MAX 64  // the reference's cap on N_samples (rendering.py:80)
 
 struct InferWs {
     float *t_cur, *t_end;
@@ -291,24 +350,37 @@ extern "C" int ngp_render_infer(const NgpNet* net, const NgpInferCfg* cfg, const
 static int infer_round(const NgpNet* net, const NgpInferCfg* cfg, const InferWs& W, const float* rays_o, const float* rays_d,
                        const uint8_t* density_bitfield, float* opacity, float* depth, float* rgb, int cur, cudaStream_t st) {
     const int n = cfg->n_rays;
-    const int S = INFER_S_MAX;  // staging capacity; the round's actual quota is computed on the device
     const int nxt = cur ^ 1;
-    const int bs = 64;
-    // the launch covers the worst case (all rays alive); blocks past the device-side count exit at once
-    const int grid = ngp_div_up(n, bs);
+    // persistent-style grids (the kernels stride over the device-side alive count): enough blocks to fill the GPU, never
+    // tens of thousands of blocks that find nothing to do in the late rounds
+    const int sms = ngp_sm_count();
+    const int grid_a = (int)min((int64_t)ngp_div_up(n, INFER_A_THREADS), (int64_t)sms * 16);
+    const int grid_w = (int)min((int64_t)ngp_div_up((int64_t)(n / INFER_WARP_MIN + 1) * 32, 128), (int64_t)sms * 16);
+    const int grid_c = (int)min((int64_t)ngp_div_up(n, 128), (int64_t)sms * 16);
     k_infer_round_begin<<<1, 1, 0, st>>>(*cfg, W.alive_cnt + cur, W.alive_cnt + nxt, W.state, W.total);
     NGP_CHECK_LAUNCH();
-    k_infer_march<<<grid, bs, (size_t)bs * S * sizeof(float2), st>>>(
-        *cfg, S, rays_o, rays_d, density_bitfield, W.t_cur, W.t_end, W.alive[cur], W.alive_cnt + cur, W.ray_start, W.ray_n,
-        W.ray_idx, W.ts, W.deltas, W.state);
+    k_infer_march<<<grid_a, INFER_A_THREADS, 0, st>>>(*cfg, rays_o, rays_d, density_bitfield, W.t_cur, W.t_end, W.alive[cur],
+                                                       W.alive_cnt + cur, W.ray_start, W.ray_n, W.ray_idx, W.ts, W.deltas, W.state);
+    NGP_CHECK_LAUNCH();
+    // the test-time step bounds use `cascades` where the train kernel uses `scale` (reference raymarching.cu:370,399)
+    const bool const_dt = cfg->exp_step_factor == 0.0f &&
+                          1.73205080757f / (float)cfg->max_samples <= (float)cfg->cascades * 3.46410161514f / (float)cfg->grid_size;
+#define NGP_LAUNCH_IW(CD, OC)                                                                                                  \
+    k_infer_march_warp<CD, OC><<<grid_w, 128, 0, st>>>(*cfg, rays_o, rays_d, density_bitfield, W.t_cur, W.t_end, W.alive[cur], \
+                                                       W.alive_cnt + cur, W.ray_start, W.ray_n, W.ray_idx, W.ts, W.deltas, W.state)
+    if (const_dt && cfg->cascades == 1) NGP_LAUNCH_IW(true, true);
+    else if (const_dt) NGP_LAUNCH_IW(true, false);
+    else if (cfg->cascades == 1) NGP_LAUNCH_IW(false, true);
+    else NGP_LAUNCH_IW(false, false);
+#undef NGP_LAUNCH_IW
     NGP_CHECK_LAUNCH();
     NgpSamples smp;
     smp.xyzs = nullptr; smp.dirs = nullptr; smp.rays_o = rays_o; smp.rays_d = rays_d; smp.ray_idx = W.ray_idx; smp.ts = W.ts;
     smp.n = cfg->max_round_samples; smp.n_dev = W.state + 2; smp.live_idx = nullptr; smp.n_live_dev = nullptr;
     int rc = ngp_net_forward(net, &smp, 1, W.sigmas, W.rgbs, nullptr, nullptr, (void*)st);
     if (rc) return rc;
-    k_infer_composite<<<grid, bs, 0, st>>>(*cfg, W.sigmas, W.rgbs, W.deltas, W.ts, W.ray_start, W.ray_n, W.t_cur, W.t_end,
-                                            W.alive[cur], W.alive_cnt + cur, opacity, depth, rgb, W.alive[nxt], W.alive_cnt + nxt);
+    k_infer_composite<<<grid_c, 128, 0, st>>>(*cfg, W.sigmas, W.rgbs, W.deltas, W.ts, W.ray_start, W.ray_n, W.t_cur, W.t_end,
+                                               W.alive[cur], W.alive_cnt + cur, opacity, depth, rgb, W.alive[nxt], W.alive_cnt + nxt);
     NGP_CHECK_LAUNCH();
     return 0;
 }

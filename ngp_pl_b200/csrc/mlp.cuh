@@ -18,8 +18,22 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4],
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// C[mt][N/8][4] = A[mt][K/16][4] x W^T, W = [N][LD] halfs in shared memory (LD = K + 8 keeps the
-// 32-bit B-fragment loads bank-conflict free).
+// ldmatrix (no transpose): four / two 8x8 b16 tiles; lane l supplies the address of row (l&7) of tile (l>>3).
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_row);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(a));
+}
+__device__ __forceinline__ void ldmatrix_x2(uint32_t& r0, uint32_t& r1, const void* smem_row) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_row);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];\n" : "=r"(r0), "=r"(r1) : "r"(a));
+}
+
+// C[mt][N/8][4] = A[mt][K/16][4] x W^T, W = [N][LD] halfs in shared memory (LD = K + 8: rows are 16-byte aligned and
+// eight consecutive rows fall into disjoint banks). The B fragments of TWO n-tiles (b0,b1 of tile j and of tile j+1) come
+// from one ldmatrix.x4 -- row n of W, k = 0..7 / 8..15 of the k-step is exactly the (k = 2q.., n = g) fragment layout --
+// instead of four 32-bit shared loads.
 template <int MT, int K, int N, int LD>
 __device__ __forceinline__ void mlp_layer(const uint32_t (&A)[MT][K / 16][4], const __half* __restrict__ W,
                                           float (&C)[MT][N / 8][4], int g, int q) {
@@ -29,14 +43,26 @@ __device__ __forceinline__ void mlp_layer(const uint32_t (&A)[MT][K / 16][4], co
         for (int j = 0; j < N / 8; ++j)
 #pragma unroll
             for (int e = 0; e < 4; ++e) C[mt][j][e] = 0.f;
+    const int lane = 4 * g + q;
+    const int lrow = lane & 7, lt = lane >> 3;  // ldmatrix: this lane addresses row lrow of tile lt
 #pragma unroll
     for (int kt = 0; kt < K / 16; ++kt) {
+        if (N / 8 >= 2) {
 #pragma unroll
-        for (int j = 0; j < N / 8; ++j) {
-            const uint32_t* w = reinterpret_cast<const uint32_t*>(W + (8 * j + g) * LD + 16 * kt + 2 * q);
-            const uint32_t b0 = w[0], b1 = w[4];
+            for (int j = 0; j + 1 < N / 8; j += 2) {
+                uint32_t b[4];
+                ldmatrix_x4(b, W + (8 * (j + (lt >> 1)) + lrow) * LD + 16 * kt + 8 * (lt & 1));
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) mma_16816(C[mt][j], A[mt][kt], b0, b1);
+                for (int mt = 0; mt < MT; ++mt) {
+                    mma_16816(C[mt][j], A[mt][kt], b[0], b[1]);
+                    mma_16816(C[mt][j + 1], A[mt][kt], b[2], b[3]);
+                }
+            }
+        } else {
+            uint32_t b0, b1;
+            ldmatrix_x2(b0, b1, W + lrow * LD + 16 * kt + 8 * (lt & 1));
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) mma_16816(C[mt][0], A[mt][kt], b0, b1);
         }
     }
 }

@@ -143,7 +143,7 @@ __device__ __forceinline__ int64_t bwd_count(const NgpSamples& s) {
     return sample_count(s);
 }
 
-__device__ __forceinline__ SampleIn load_sample(const NgpSamples& s, int64_t i, bool valid) {
+__device__ __forceinline__ SampleIn load_sample(const NgpSamples& s, int64_t i, bool& valid) {
     SampleIn o;
     if (!valid) {
         o.x = o.y = o.z = 0.f;
@@ -152,6 +152,12 @@ __device__ __forceinline__ SampleIn load_sample(const NgpSamples& s, int64_t i, 
     }
     if (s.ray_idx) {
         const int r = __ldg(s.ray_idx + i);
+        if (r < 0) {  // an unused slot of a rectangular (ray, slot) layout (ngp_render_infer's warp-per-ray rounds)
+            valid = false;
+            o.x = o.y = o.z = 0.f;
+            o.dx = 0.f; o.dy = 0.f; o.dz = 1.f;
+            return o;
+        }
         const float t = __ldg(s.ts + i);
         o.dx = __ldg(s.rays_d + 3 * r); o.dy = __ldg(s.rays_d + 3 * r + 1); o.dz = __ldg(s.rays_d + 3 * r + 2);
         // same rounding as the marcher's sample position (march.cuh: x = fma(d, t, o))
@@ -182,44 +188,22 @@ __device__ __forceinline__ void to_unit(const NgpNet& net, const SampleIn& s, fl
 
 // Encode the rows this lane owns into the A fragments of the first density layer.
 // Lane (g,q) owns rows {g, g+8} of each 16-row tile and levels {q, q+4, q+8, q+12}.
-template <int MT, bool PAIRED = false, int DEPTH = 1>
+template <int MT>
 __device__ __forceinline__ void encode_rows(const NgpNet& net, const uint32_t* __restrict__ table,
                                             const float (&u)[MT][2][3], const bool (&valid)[MT][2],
                                             uint32_t (&featA)[MT][2][4], int q) {
-    if (DEPTH <= 1) {
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
+        for (int h = 0; h < 2; ++h)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int level = 4 * j + q;
-                    float2 f = make_float2(0.f, 0.f);
-                    if (valid[mt][h] && level < net.meta.n_levels)
-                        f = PAIRED ? grid_lookup_paired(table, net.meta, level, u[mt][h][0], u[mt][h][1], u[mt][h][2])
-                                   : grid_lookup(table, net.meta, level, u[mt][h][0], u[mt][h][1], u[mt][h][2]);
-                    featA[mt][j >> 1][2 * (j & 1) + h] = pack_half2(f.x, f.y);
-                }
-        return;
-    }
-    // software pipeline over the 8*MT lookups of this lane: lookup t+1 is fetched before lookup t is reduced
-    constexpr int T = 8 * MT;
-    GridFetch<PAIRED> cur, nxt;
-    auto fetch = [&](GridFetch<PAIRED>& f, int t) {
-        const int mt = t >> 3, h = (t >> 2) & 1, j = t & 3;
-        const int level = 4 * j + q;
-        grid_fetch<PAIRED>(f, table, net.meta, level < net.meta.n_levels ? level : 0, u[mt][h][0], u[mt][h][1], u[mt][h][2],
-                           valid[mt][h] && level < net.meta.n_levels);
-    };
-    fetch(cur, 0);
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-        if (t + 1 < T) fetch(nxt, t + 1);
-        const float2 f = grid_reduce<PAIRED>(cur);
-        const int mt = t >> 3, h = (t >> 2) & 1, j = t & 3;
-        featA[mt][j >> 1][2 * (j & 1) + h] = pack_half2(f.x, f.y);
-        cur = nxt;
-    }
+            for (int j = 0; j < 4; ++j) {
+                const int level = 4 * j + q;
+                float2 f = make_float2(0.f, 0.f);
+                if (valid[mt][h] && level < net.meta.n_levels)
+                    f = grid_lookup(table, net.meta, level, u[mt][h][0], u[mt][h][1], u[mt][h][2]);
+                featA[mt][j >> 1][2 * (j & 1) + h] = pack_half2(f.x, f.y);
+            }
 }
 
 // SH-4 of the normalised direction, as the A fragment k-tile 0 of the rgb net input.
@@ -238,7 +222,7 @@ __device__ __forceinline__ float hi_half(uint32_t u) { return __half2float(__ush
 // -------------------------------------------------------------------------------------------------
 // forward
 // -------------------------------------------------------------------------------------------------
-template <int FWD_MT, int FWD_THREADS, int MIN_BLOCKS, bool PAIRED, int DEPTH>
+template <int FWD_MT, int FWD_THREADS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(FWD_THREADS, MIN_BLOCKS)
 k_ngp_fwd(const NgpNet net, const NgpSamples smp, const int want_rgb, float* __restrict__ sigmas, float* __restrict__ rgbs,
           __half* __restrict__ h_out, uint4* __restrict__ feat_save, int* __restrict__ sched) {
@@ -275,7 +259,7 @@ k_ngp_fwd(const NgpNet net, const NgpSamples smp, const int want_rgb, float* __r
             }
 
         uint32_t featA[FWD_MT][2][4];
-        encode_rows<FWD_MT, PAIRED, DEPTH>(net, table, u, valid, featA, q);
+        encode_rows<FWD_MT>(net, table, u, valid, featA, q);
 
         if (feat_save) {
 #pragma unroll
@@ -371,23 +355,8 @@ static int launch_fwd(const NgpNet* net, const NgpSamples* smp, int want_rgb, fl
     const int64_t cap = (int64_t)ngp_sm_count() * MIN_BLOCKS;
     const int grid = (int)(want < cap ? want : cap);
     int* sched = sched_slot(st);
-    // NGP_GATHER_PAIRED / NGP_GATHER_DEPTH (env, read once): aligned 8-byte x-pair loads in the hash gather; software
-    // pipelining of the lookups (hashgrid.cuh)
-    static int paired = -1, depth = -1;
-    if (paired < 0) {
-        const char* e = getenv("NGP_GATHER_PAIRED");
-        paired = e ? atoi(e) : 0;
-        e = getenv("NGP_GATHER_DEPTH");
-        depth = e ? atoi(e) : 1;
-    }
-#define NGP_LAUNCH_FWD(P, D)                                                                                              \
-    k_ngp_fwd<MT, THREADS, MIN_BLOCKS, P, D><<<grid, THREADS, 0, st>>>(*net, *smp, want_rgb, sigmas, rgbs, (__half*)h_out, \
-                                                                       (uint4*)feat_save, sched)
-    if (paired && depth > 1) NGP_LAUNCH_FWD(true, 2);
-    else if (paired) NGP_LAUNCH_FWD(true, 1);
-    else if (depth > 1) NGP_LAUNCH_FWD(false, 2);
-    else NGP_LAUNCH_FWD(false, 1);
-#undef NGP_LAUNCH_FWD
+    k_ngp_fwd<MT, THREADS, MIN_BLOCKS><<<grid, THREADS, 0, st>>>(*net, *smp, want_rgb, sigmas, rgbs, (__half*)h_out,
+                                                                 (uint4*)feat_save, sched);
     return 0;
 }
 
@@ -1017,7 +986,7 @@ k_ngp_bwd2(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_
 #define SCATTER_THREADS 256
 __global__ void __launch_bounds__(SCATTER_THREADS)
 k_grid_scatter_merged(const NgpNet net, const NgpSamples smp, const uint32_t* __restrict__ dfeat, const int64_t dfeat_stride,
-                      const float* __restrict__ loss_scale, float* __restrict__ grad_table, const int paired) {
+                      const float* __restrict__ loss_scale, float* __restrict__ grad_table) {
     const int lane = threadIdx.x & 31;
     const int64_t n = bwd_count(smp);
     const float inv_scale = loss_scale ? 1.0f / *loss_scale : 1.0f;
@@ -1025,7 +994,7 @@ k_grid_scatter_merged(const NgpNet net, const NgpSamples smp, const uint32_t* __
     const int n_levels = net.meta.n_levels;
 
     for (int64_t s = blockIdx.x * (int64_t)SCATTER_THREADS + threadIdx.x; s < n_pad; s += (int64_t)gridDim.x * SCATTER_THREADS) {
-        const bool valid = s < n;
+        bool valid = s < n;
         // the sample position is computed once and reused for all levels (dfeat is indexed by s, the position by
         // the sample it stands for)
         const SampleIn sm = load_sample(smp, (valid && smp.live_idx) ? (int64_t)__ldg(smp.live_idx + s) : s, valid);
@@ -1088,14 +1057,7 @@ k_grid_scatter_merged(const NgpNet net, const NgpSamples smp, const uint32_t* __
                 uint32_t idx[8];
                 grid_corner_indices(c, res, entries, hashed, idx);
                 const float* lvl = grad_table + 2 * (size_t)off;
-                if (paired) {
-                    grid_scatter_cell_paired(lvl, idx, acc);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        red_add_f32x2(const_cast<float*>(reinterpret_cast<const float*>(entry_ptr<8>(lvl, idx[k]))), acc[2 * k],
-                                      acc[2 * k + 1]);
-                }
+                grid_scatter_cell_paired(lvl, idx, acc);  // 16-byte reductions for aligned x-corner pairs, 8-byte otherwise
             }
         }
     }
@@ -1170,14 +1132,8 @@ extern "C" int ngp_net_backward_scatter(const NgpNet* net, const NgpSamples* smp
     int64_t gx = (smp->n + SCATTER_THREADS - 1) / SCATTER_THREADS;
     const int64_t cap = (int64_t)ngp_sm_count() * 8;
     if (gx > cap) gx = cap;
-    // NGP_SCATTER_PAIRED (env, read once): 16-byte reductions for aligned x-corner pairs (hashgrid.cuh)
-    static int paired = -1;
-    if (paired < 0) {
-        const char* e = getenv("NGP_SCATTER_PAIRED");
-        paired = e ? atoi(e) : 0;
-    }
     k_grid_scatter_merged<<<(unsigned)gx, SCATTER_THREADS, 0, (cudaStream_t)stream>>>(
-        *net, *smp, (const uint32_t*)workspace, n_mtiles * 16, loss_scale, grad_enc + NGP_DENSITY_MLP_PARAMS, paired);
+        *net, *smp, (const uint32_t*)workspace, n_mtiles * 16, loss_scale, grad_enc + NGP_DENSITY_MLP_PARAMS);
     NGP_CHECK_LAUNCH();
     return 0;
 }

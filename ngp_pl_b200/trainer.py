@@ -137,9 +137,6 @@ class Trainer:
         self.random_bg = bool(random_bg)   # reference rendering.py:153-161 (one random colour per training batch)
         self.erode = bool(erode)           # reference networks.py:258-260 / train.py:163 (needs model.count_grid)
         self.lr_schedule = lr_schedule     # e.g. CosineAnnealingLR(lr, T_max=30, steps_per_epoch=1000)
-        # captured compute / optimiser kernels get a higher stream priority than the run-ahead march (NGP_PRIORITY=0: off)
-        import os
-        self.prioritize = os.environ.get("NGP_PRIORITY", "1") != "0"
         self._n_gbuf = 2 if self.ddp in ("p2p", "nvls") else 1
         self._gcur = 0
         L = _lib.lib()
@@ -554,15 +551,13 @@ class Trainer:
         every launch recorded while capturing) + recorded launches x graph replays"""
         return int(_lib.lib().ngp_launch_count()) + self.graph_launches
 
-    def _capture_graph(self, fn, high=False):
-        """`high`: capture on a high-priority stream -- kernel nodes keep the priority of the stream they were captured on,
-        so the critical path (compute, optimiser) wins the block scheduler over the next step's march, which then only
-        fills the SM resources the critical path leaves free instead of delaying its kernels at every kernel boundary."""
+    def _capture_graph(self, fn):
+        # (capturing the compute / optimiser graphs on a high-priority stream so that their kernels win the block scheduler
+        # over the run-ahead march was measured: no effect on the step, 0.3840 vs 0.3853 ms, profiles/r02_variant_sweep.txt)
         g = torch.cuda.CUDAGraph()
         g.register_generator_state(self.gen)
         n0 = int(_lib.lib().ngp_launch_count())
-        st = (self._cap_hi if high else self._cap_lo) if self.prioritize else None
-        with torch.cuda.graph(g, stream=st):
+        with torch.cuda.graph(g):
             fn()
         self._graph_nodes[id(g)] = int(_lib.lib().ngp_launch_count()) - n0
         return g
@@ -597,8 +592,6 @@ class Trainer:
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
         self.g_prepare, self.g_compute, self.g_update = [], [], None
-        self._cap_hi = torch.cuda.Stream(dev, priority=-1)
-        self._cap_lo = torch.cuda.Stream(dev, priority=0)
         keep = (self._cur, self._gcur)
         for i in range(2):
             self._cur = i
@@ -606,16 +599,16 @@ class Trainer:
             per_buf = []
             for b in range(self._n_gbuf):
                 self._gcur = b
-                per_buf.append(self._capture_graph(self._compute, high=True))
+                per_buf.append(self._capture_graph(self._compute))
             self.g_compute.append(per_buf)
         if self.ddp in ("p2p", "nvls"):
             self.g_update = []
             for b in range(self._n_gbuf):
                 self._gcur = b
-                self.g_update.append(self._capture_graph(self._launch_fused, high=True))
+                self.g_update.append(self._capture_graph(self._launch_fused))
         elif self.ddp not in ("p2p_host", "zero"):
             self._gcur = 0
-            self.g_update = [self._capture_graph(self.optimizer_step, high=True)]
+            self.g_update = [self._capture_graph(self.optimizer_step)]
         self._cur, self._gcur = keep
         self.graph = True
         self._graph_samples = sample

@@ -70,13 +70,21 @@ def main():
     curve = {}
     torch.cuda.synchronize()
     t0 = time.perf_counter()
+    near = set()
+    for c in cps:
+        near.update(range(c - 49, c + 1))
+    mses = []
     for step in range(1, steps + 1):
         tr.train_step()
+        if step in near:  # train PSNR = mean MSE of the 50 batches before a checkpoint (one batch alone is +-0.5 dB noise)
+            mses.append(tr.scalars[2].item() / (3 * N_RAYS))
         if step in cps:
             torch.cuda.synchronize()
             p, views = eval_psnr(lambda o, d: render(model, o, d, test_time=True), scene, a.views, a.res)
-            curve[str(step)] = {"test_psnr": p, "views": views, "train_psnr_last_batch": tr.stats()["psnr"], "lr": tr.lr}
-            print("b200 step %d: test %.3f dB  train(last batch) %.3f dB  lr %.2e" % (step, p, tr.stats()["psnr"], tr.lr), flush=True)
+            tp = -10 * math.log10(max(float(np.mean(mses[-50:])), 1e-12))
+            curve[str(step)] = {"test_psnr": p, "views": views, "train_psnr_mean50": tp, "lr": tr.lr,
+                                "samples_per_ray": tr.stats()["rm_samples"] / N_RAYS}
+            print("b200 step %d: test %.3f dB  train(mean of 50 batches) %.3f dB  lr %.2e" % (step, p, tp, tr.lr), flush=True)
     res["b200"] = curve
     res["b200_wall_s"] = time.perf_counter() - t0
     del tr
@@ -100,6 +108,7 @@ def main():
             with torch.autocast("cuda", dtype=torch.float16):
                 return ref.render(m2, o, d, test_time=True)
         curve = {}
+        mses = []
         t0 = time.perf_counter()
         for step in range(1, steps + 1):
             o, d, rgb = bank2.sample(N_RAYS)
@@ -112,18 +121,22 @@ def main():
             scaler.scale(loss).backward()
             scaler.step(opt)
             scaler.update()
-            if sch is not None and step % 1000 == 0:
-                sch.step()  # PL steps the scheduler at the end of every (1000-step) epoch
+            if step in near:
+                mses.append(((r["rgb"].float() - rgb) ** 2).mean().item())
             if step in cps:
                 torch.cuda.synchronize()
                 p, views = eval_psnr(ref_render, scene, a.views, a.res)
-                tp = -10 * math.log10(max(((r["rgb"].float() - rgb) ** 2).mean().item(), 1e-12))
-                curve[str(step)] = {"test_psnr": p, "views": views, "train_psnr_last_batch": tp, "lr": opt.param_groups[0]["lr"]}
-                print("reference step %d: test %.3f dB  train(last batch) %.3f dB" % (step, p, tp), flush=True)
+                tp = -10 * math.log10(max(float(np.mean(mses[-50:])), 1e-12))
+                curve[str(step)] = {"test_psnr": p, "views": views, "train_psnr_mean50": tp, "lr": opt.param_groups[0]["lr"],
+                                    "samples_per_ray": float(r["rm_samples"]) / N_RAYS}
+                print("reference step %d: test %.3f dB  train(mean of 50 batches) %.3f dB" % (step, p, tp), flush=True)
+            if sch is not None and step % 1000 == 0:
+                sch.step()  # PL steps the scheduler at the end of every (1000-step) epoch
         res["reference"] = curve
         res["reference_wall_s"] = time.perf_counter() - t0
         res["delta_db"] = {k: res["b200"][k]["test_psnr"] - curve[k]["test_psnr"] for k in curve}
         res["delta_db_final"] = res["delta_db"][str(steps)]
+        res["delta_train_db"] = {k: res["b200"][k]["train_psnr_mean50"] - curve[k]["train_psnr_mean50"] for k in curve}
     print(json.dumps(res))
     if a.out:
         json.dump(res, open(a.out, "w"), indent=1)
