@@ -53,14 +53,16 @@ __global__ void k_infer_init(const NgpInferCfg cfg, const float* __restrict__ ra
 // computed from the device-side alive count. N_alive * N_samples <= max(N_rays, min_samples * N_alive) <= 4 * N_rays, the
 // capacity of the per-round sample buffers (max_round_samples), so the quota never has to be clipped.
 // Two marching regimes (both kernels are launched every round, the one whose regime it is not exits at once):
-//   N_samples <  INFER_WARP_MIN : many rays, few samples each -> one THREAD per ray, samples staged in shared memory and
-//                                 appended compactly (one atomic per warp);
-//   N_samples >= INFER_WARP_MIN : few rays (<= N_rays / 8), many samples each -> one WARP per ray (march_ray_warp, 32 chain
-//                                 points probed side by side), samples written straight to the ray's own N_samples slots,
-//                                 unused slots marked ray_idx = -1 (the network kernel skips their gathers).
+//   more than half of the rays alive (the first round(s): every ray walks from the box entry to its first samples, and
+//       one visit per empty CELL is ~5x less work than probing every chain point) -> one THREAD per ray, samples staged
+//       in shared memory and appended compactly (one atomic per warp);
+//   otherwise -> one WARP per ray (march_ray_warp: 32 chain points probed side by side; no lane waits for a neighbour
+//       that still walks through empty space, which is what made the thread-per-ray kernel 110-150 us per round at 2-7
+//       samples per ray, profiles/r02_infer_launches_before.md), samples written straight to the ray's own N_samples slots,
+//       unused slots marked ray_idx = -1 (the network kernel skips their gathers).
 // state: [0] N_samples of this round (0 = loop over)  [1] `samples` so far  [2] slots the network evaluates this round
-//        [3] rounds run  [4] samples marched this round
-#define INFER_WARP_MIN 8
+//        [3] rounds run  [4] samples marched this round  [5] 1 = warp-per-ray regime
+#define INFER_STAGE 4  // staging slots per thread in the thread-per-ray regime (N_samples <= max(1, min_samples) = 4 there)
 __global__ void k_infer_round_begin(const NgpInferCfg cfg, int* __restrict__ alive_count, int* __restrict__ next_count,
                                     int* __restrict__ state, int64_t* __restrict__ total) {
     *total += state[4];
@@ -80,23 +82,26 @@ __global__ void k_infer_round_begin(const NgpInferCfg cfg, int* __restrict__ ali
         if (share < S) S = (int)(share < 1 ? 1 : share);
         state[1] += S;
         state[3] += 1;
-        if (S >= INFER_WARP_MIN) state[2] = n_alive * S;  // rectangular slots; the thread-per-ray regime counts as it appends
+        const bool warp_regime = 2 * (int64_t)n_alive <= cfg.n_rays || S > INFER_STAGE;
+        state[5] = warp_regime ? 1 : 0;
+        if (warp_regime) state[2] = n_alive * S;  // rectangular slots; the thread-per-ray regime counts as it appends
     }
     state[0] = S;
 }
 
-// one round of marching, thread-per-ray regime: every alive ray takes up to S < INFER_WARP_MIN occupied samples (staged in
+// one round of marching, thread-per-ray regime: every alive ray takes up to S <= INFER_STAGE occupied samples (staged in
 // shared memory), then the warp claims a contiguous range of the compact sample arrays with one atomic.
 #define INFER_A_THREADS 128
+template <bool CONST_DT, bool ONE_CASCADE>
 __global__ void __launch_bounds__(INFER_A_THREADS)
 k_infer_march(const NgpInferCfg cfg, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
               const uint8_t* __restrict__ bitfield, float* __restrict__ t_cur, const float* __restrict__ t_end,
               const int* __restrict__ alive, const int* __restrict__ alive_count, int* __restrict__ ray_start,
               int* __restrict__ ray_n, int* __restrict__ ray_idx, float* __restrict__ ts, float* __restrict__ deltas,
               int* __restrict__ state) {
-    __shared__ float2 stage[INFER_A_THREADS][INFER_WARP_MIN];
+    __shared__ float2 stage[INFER_A_THREADS][INFER_STAGE];
     const int S = state[0];
-    if (S <= 0 || S >= INFER_WARP_MIN) return;
+    if (S <= 0 || state[5]) return;
     const int lane = threadIdx.x & 31;
     const int n_alive = *alive_count;
     const MarchConst c = make_march_const(bitfield, cfg.cascades, cfg.grid_size, cfg.max_samples, cfg.scale, cfg.exp_step_factor,
@@ -113,9 +118,9 @@ k_infer_march(const NgpInferCfg cfg, const float* __restrict__ rays_o, const flo
                                                 rays_d[3 * r], rays_d[3 * r + 1], rays_d[3 * r + 2]);
             t = t_cur[r];
             const float t2 = t_end[r];
-            float x, y, z, dt;
+            float dt;
             while (t < t2 && n < S) {
-                if (march_visit(ray, c, t, x, y, z, dt)) {
+                if (march_visit_t<CONST_DT, ONE_CASCADE>(ray, c, t, dt)) {
                     my[n] = make_float2(t, dt);
                     t = __fadd_rn(t, dt);
                     ++n;
@@ -149,8 +154,8 @@ k_infer_march(const NgpInferCfg cfg, const float* __restrict__ rays_o, const flo
     }
 }
 
-// warp-per-ray regime (S >= INFER_WARP_MIN): same sample sequence, 32 chain points probed at a time (march_ray_warp);
-// ray i owns slots [i*S, (i+1)*S)
+// warp-per-ray regime: same sample sequence, 32 chain points probed at a time (march_ray_warp); ray i owns slots
+// [i*S, (i+1)*S). The next ray's index, origin, direction and interval are fetched while the current one is marched.
 template <bool CONST_DT, bool ONE_CASCADE>
 __global__ void __launch_bounds__(128)
 k_infer_march_warp(const NgpInferCfg cfg, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
@@ -159,19 +164,33 @@ k_infer_march_warp(const NgpInferCfg cfg, const float* __restrict__ rays_o, cons
                    int* __restrict__ ray_n, int* __restrict__ ray_idx, float* __restrict__ ts, float* __restrict__ deltas,
                    int* __restrict__ state) {
     const int S = state[0];
-    if (S < INFER_WARP_MIN) return;
+    if (S <= 0 || !state[5]) return;
     const int lane = threadIdx.x & 31;
     const int n_alive = *alive_count;
     const MarchConst c = make_march_const(bitfield, cfg.cascades, cfg.grid_size, cfg.max_samples, cfg.scale, cfg.exp_step_factor,
                                           (float)cfg.cascades);
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     int marched = 0;
-    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_alive; i += n_warps) {
-        const int r = alive[i];
-        const MarchRay ray = make_march_ray(rays_o[3 * r], rays_o[3 * r + 1], rays_o[3 * r + 2],
-                                            rays_d[3 * r], rays_d[3 * r + 1], rays_d[3 * r + 2]);
-        const float t = t_cur[r];
-        const float t2 = t_end[r];
+    // lanes 0..7 of the warp hold {ox,oy,oz,dx,dy,dz,t,t2} of the NEXT ray (one load each), broadcast when its turn comes
+    int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int r_next = i < n_alive ? alive[i] : -1;
+    auto fetch = [&](int r) -> float {
+        if (r < 0 || lane > 7) return 0.f;
+        if (lane < 3) return rays_o[3 * r + lane];
+        if (lane < 6) return rays_d[3 * r + lane - 3];
+        return lane == 6 ? t_cur[r] : t_end[r];
+    };
+    float v_next = fetch(r_next);
+    for (; i < n_alive; i += n_warps) {
+        const int r = r_next;
+        const float v = v_next;
+        const int i2 = i + n_warps;
+        r_next = i2 < n_alive ? alive[i2] : -1;
+        v_next = fetch(r_next);
+        const MarchRay ray = make_march_ray(__shfl_sync(0xffffffffu, v, 0), __shfl_sync(0xffffffffu, v, 1), __shfl_sync(0xffffffffu, v, 2),
+                                            __shfl_sync(0xffffffffu, v, 3), __shfl_sync(0xffffffffu, v, 4), __shfl_sync(0xffffffffu, v, 5));
+        const float t = __shfl_sync(0xffffffffu, v, 6);
+        const float t2 = __shfl_sync(0xffffffffu, v, 7);
         const int64_t base = (int64_t)i * S;
         float resume = t;
         const int n = march_ray_warp<CONST_DT, ONE_CASCADE>(ray, c, t, t2, S, lane, [&](int k, float tk, float dk) {
@@ -355,16 +374,23 @@ static int infer_round(const NgpNet* net, const NgpInferCfg* cfg, const InferWs&
     // tens of thousands of blocks that find nothing to do in the late rounds
     const int sms = ngp_sm_count();
     const int grid_a = (int)min((int64_t)ngp_div_up(n, INFER_A_THREADS), (int64_t)sms * 16);
-    const int grid_w = (int)min((int64_t)ngp_div_up((int64_t)(n / INFER_WARP_MIN + 1) * 32, 128), (int64_t)sms * 16);
+    const int grid_w = (int)min((int64_t)ngp_div_up((int64_t)(n / 2 + 1) * 32, 128), (int64_t)sms * 16);
     const int grid_c = (int)min((int64_t)ngp_div_up(n, 128), (int64_t)sms * 16);
     k_infer_round_begin<<<1, 1, 0, st>>>(*cfg, W.alive_cnt + cur, W.alive_cnt + nxt, W.state, W.total);
-    NGP_CHECK_LAUNCH();
-    k_infer_march<<<grid_a, INFER_A_THREADS, 0, st>>>(*cfg, rays_o, rays_d, density_bitfield, W.t_cur, W.t_end, W.alive[cur],
-                                                       W.alive_cnt + cur, W.ray_start, W.ray_n, W.ray_idx, W.ts, W.deltas, W.state);
     NGP_CHECK_LAUNCH();
     // the test-time step bounds use `cascades` where the train kernel uses `scale` (reference raymarching.cu:370,399)
     const bool const_dt = cfg->exp_step_factor == 0.0f &&
                           1.73205080757f / (float)cfg->max_samples <= (float)cfg->cascades * 3.46410161514f / (float)cfg->grid_size;
+#define NGP_LAUNCH_IA(CD, OC)                                                                                                  \
+    k_infer_march<CD, OC><<<grid_a, INFER_A_THREADS, 0, st>>>(*cfg, rays_o, rays_d, density_bitfield, W.t_cur, W.t_end,        \
+                                                              W.alive[cur], W.alive_cnt + cur, W.ray_start, W.ray_n, W.ray_idx, \
+                                                              W.ts, W.deltas, W.state)
+    if (const_dt && cfg->cascades == 1) NGP_LAUNCH_IA(true, true);
+    else if (const_dt) NGP_LAUNCH_IA(true, false);
+    else if (cfg->cascades == 1) NGP_LAUNCH_IA(false, true);
+    else NGP_LAUNCH_IA(false, false);
+#undef NGP_LAUNCH_IA
+    NGP_CHECK_LAUNCH();
 #define NGP_LAUNCH_IW(CD, OC)                                                                                                  \
     k_infer_march_warp<CD, OC><<<grid_w, 128, 0, st>>>(*cfg, rays_o, rays_d, density_bitfield, W.t_cur, W.t_end, W.alive[cur], \
                                                        W.alive_cnt + cur, W.ray_start, W.ray_n, W.ray_idx, W.ts, W.deltas, W.state)

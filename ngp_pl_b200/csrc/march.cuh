@@ -221,6 +221,19 @@ __device__ __forceinline__ MarchProbe march_probe(const MarchRay& r, const March
     return o;
 }
 
+// Serial visit with the specialisations of march_probe (ONE_CASCADE drops the two frexpf, the scalbnf and the division;
+// CONST_DT the multiply / clamp of the step): same values, same roundings as march_visit().
+template <bool CONST_DT, bool ONE_CASCADE>
+__device__ __forceinline__ bool march_visit_t(const MarchRay& r, const MarchConst& c, float& t, float& dt) {
+    const MarchProbe pr = march_probe<ONE_CASCADE>(r, c, t);
+    dt = pr.dt;
+    if (pr.occ) return true;
+    do {
+        t = __fadd_rn(t, CONST_DT ? c.dt_lo : march_dt(t, c));
+    } while (t < pr.t_target);
+    return false;
+}
+
 // March one ray with a full warp. emit(k, t, dt) is called by the lane owning the k-th sample
 // (k = 0.. in ray order). Returns the number of samples (same in every lane) and leaves in t_resume the
 // chain point the serial marcher would visit next (what raymarching_test stores back into hits_t).
