@@ -70,7 +70,7 @@ def parse():
                     help="N>1 gradient exchange. p2p: ONE self-synchronising NVLink kernel (reduce-scatter + sharded Adam + "
                          "all-gather, in-kernel barriers, in the step's CUDA graph); nvls: the same through the NVSwitch multicast "
                          "mapping; p2p_host: round 1's host-barrier variant; zero: NCCL reduce_scatter/all_gather; nccl: "
-                         "all-reduce + full Adam (the reference's DDP). auto = p2p")
+                         "all-reduce + full Adam (the reference's DDP). auto = p2p for 2 GPUs, nvls beyond")
     return ap.parse_args()
 
 
@@ -362,9 +362,13 @@ def exchange_check(tr, world, rank):
     torch.cuda.synchronize()
     dist.barrier()
     dP, dH = float(t[0]), float(t[1])
-    tol = 0.0 if world == 2 else 1e-6
+    # N = 2: bitwise (a + b == b + a). Beyond: only the fp32 summation order differs from NCCL's; a parameter that crosses an
+    # fp16 rounding boundary moves the working copy by one fp16 ulp (<= 2^-10 of the parameter scale)
+    scale = max(1.0, float(tr.P.abs().max()))
+    tol, tol_half = (0.0, 0.0) if world == 2 else (2e-6 * scale, 2.0 ** -10 * scale)
     return {"against": "NCCL all_reduce + full-size ngp_adam_step", "max_abs_diff_params_owned_shard": dP,
-            "max_abs_diff_fp16_working_copy": dH, "bitwise": dP == 0.0 and dH == 0.0, "ok": dP <= tol and dH <= max(tol * 10, 0.0)}
+            "max_abs_diff_fp16_working_copy": dH, "bitwise": dP == 0.0 and dH == 0.0, "ok": dP <= tol and dH <= tol_half,
+            "tolerance": "bitwise" if world == 2 else "2e-6 on fp32 parameters, one fp16 ulp on the working copy (summation order)"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -381,7 +385,9 @@ def run_b200(args):
     scene = make_scene(args.workload)
     esf = scene.exp_step_factor
     bank = synth.RayBank(scene, n_images=N_TRAIN_IMAGES, device=dev, seed=rank)  # every rank: own images order/sampling
-    ddp_mode = args.ddp if args.ddp != "auto" else "p2p"
+    # auto: the peer-load kernel for 2 GPUs, the NVSwitch-reduced variant beyond (measured: N=2 0.390 vs 0.425 ms/step,
+    # N=8 0.447 vs 0.431; profiles/r02_bench_n2_*.json, r02_bench_n8_*.json); falls back to p2p without a multicast mapping
+    ddp_mode = args.ddp if args.ddp != "auto" else ("p2p" if world <= 2 else "nvls")
     tkw = dict(n_rays=n_rays, lr=1e-2, exp_step_factor=esf, bg=(scene.bg,) * 3, process_group=pg, world_size=world, rank=rank, seed=rank)
     model = NGP(scene.scale).to(dev)
     try:

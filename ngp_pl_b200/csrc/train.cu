@@ -862,7 +862,15 @@ extern "C" int ngp_adam_step_fused(int world, int rank, const uint64_t* peer_gra
     int64_t work = hi4 - lo4;
     if (zero_buf && n4 > work) work = n4;
     int grid = ngp_div_up(work > 0 ? work : 1, 256 * 4);
-    const int cap = ngp_sm_count() * 3;
+    // resident blocks per SM: 3 fills the SM's registers (fastest for the kernel alone); NGP_FUSED_BLOCKS_PER_SM (env, read
+    // once) lowers it so that the run-ahead march of the next step can share the SMs while this kernel waits at its barriers
+    static int per_sm = -1;
+    if (per_sm < 0) {
+        const char* e = getenv("NGP_FUSED_BLOCKS_PER_SM");
+        per_sm = e ? atoi(e) : 3;
+        if (per_sm < 1 || per_sm > 3) per_sm = 3;
+    }
+    const int cap = ngp_sm_count() * per_sm;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
 #define NGP_LAUNCH_FUSED(W)                                                                                                \

@@ -36,7 +36,11 @@ def main():
     n = tr.n_params
     L = _lib.lib()
     st = torch.cuda.current_stream().cuda_stream
-    tol = 0.0 if world == 2 else 1e-6
+    # N = 2: a + b == b + a, bitwise. N > 2: the fp32 summation order differs from NCCL's (a few 1e-7 on parameters of
+    # magnitude <= 1), and a parameter that lands on the other side of an fp16 rounding boundary moves the fp16 working
+    # copy by one fp16 ulp (<= 2^-10 relative)
+    tol = 0.0 if world == 2 else 2e-6
+    tol_half = 0.0 if world == 2 else 2.0 ** -10
     ok = True
 
     def nccl_adam(Pa, Ga, Ma, Va, Pha, step_a):
@@ -60,7 +64,9 @@ def main():
         dist.broadcast(ref_p, src=0)
         same = bool((ref_h == tr.Ph).all()) and bool((ref_p == tr.P).all())
         full_h = bool((tr.Ph.float() - tr.P).abs().max().item() < 1e-2 * max(1.0, tr.P.abs().max().item()))
-        good = dP <= tol and dH <= tol * 10 and dM <= tol and gz == 0.0 and int(tr.step_dev) == int(step_a) and same and full_h
+        scale = max(1.0, Pa.abs().max().item())
+        good = dP <= tol * scale and dH <= tol_half * scale and dM <= tol * scale and gz == 0.0 and int(tr.step_dev) == int(step_a) \
+            and same and full_h
         print("rank %d %s [%s]: shard max|dP| %.3e |dPh| %.3e |dM| %.3e  grad cleared %s  ranks identical %s  Ph==half(P) %s  step %d -> %s"
               % (rank, tag, mode, dP, dH, dM, gz == 0.0, same, full_h, int(tr.step_dev), "OK" if good else "MISMATCH"), flush=True)
         return good
