@@ -229,7 +229,8 @@ typedef struct {
     float* stage_t;               /* (n_rays*max_samples) marcher staging */
     float* stage_dt;              /* (n_rays*max_samples) */
     int32_t* n_samples;           /* (n_rays) marched samples per ray == rays_a[:,2] */
-    int32_t* offsets;             /* (n_rays) exclusive prefix sum == rays_a[:,1] */
+    int32_t* offsets;             /* (n_rays) first sample of the ray == rays_a[:,1]; segments are handed out in arrival order
+                                     (like the reference's atomic rays_a, raymarching.cu:237-241) and partition [0, total) */
     int32_t* counters;            /* int32[8]: [0] marched samples (rm_samples), [1] composited (vr_samples) of the step in flight;
                                      [2],[3] the same, snapshotted by ngp_nerf_loss_grad for the last completed step;
                                      [4] append cursor of live_idx while the compositing backward runs (0 otherwise), [5] length of live_idx,
@@ -259,7 +260,8 @@ typedef struct {
                                      reference's random_bg draws one colour per training batch, rendering.py:153-161) */
 } NgpTrainBuffers;
 
-size_t ngp_train_scan_temp_bytes(int n_rays); /* NgpTrainBuffers.scan_temp size */
+size_t ngp_train_scan_temp_bytes(int n_rays); /* NgpTrainBuffers.scan_temp size; the buffer must be ZERO-INITIALISED once by the caller
+                                                 (accumulators of the march kernel's segment allocation, re-armed by the kernel) */
 
 /* forward = __render_rays_train (models/rendering.py:121-163) incl. the AABB test and near clamp of render() (:25-29):
  * fills per-ray rgb/opacity/depth (+ws) and everything the backward needs */

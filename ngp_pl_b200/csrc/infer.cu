@@ -3,31 +3,80 @@
 //
 // The reference loops on the host: march N more samples for every alive ray, evaluate the network,
 // composite, drop converged rays (boolean-mask compaction => >= 3 host syncs per round, tens of rounds
-// per image). Here the alive list (ping-pong), the per-round sample counts and the convergence test all
-// stay on the device. Per round every alive ray receives the reference's sample budget
-// max(min(N_rays / N_alive, 64), min_samples) (rendering.py:73), computed ON the device from the alive
-// counter and clamped to a fair share of the sample capacity, so long rays are never starved. The host
-// enqueues `n_rounds` rounds at a time and reads only the alive counter between batches
-// (ngp_render_infer: first_round / n_rounds / finish / alive_count_out). Each ray still sees exactly the
-// reference's sample sequence (raymarching_test_kernel semantics, incl. its `cascades`-as-scale quirk) and
-// the same front-to-back accumulation order, so results differ from the reference only by the fp16-level
-// network difference and by where the chunk boundaries fall (T is resumed as 1 - opacity,
-// volumerendering.cu:230).
+// per image). Here the alive list (ping-pong), the per-round sample quota and the convergence test all
+// stay on the device. Per round every alive ray receives the reference's sample quota
+// max(min(N_rays // N_alive, 64), min_samples) (rendering.py:73,80), computed ON the device from the alive
+// counter, and a ray leaves the alive list exactly when the reference's composite_test_fw drops it
+// (volumerendering.cu:221-248) -- so the rounds, the per-round quotas and total_samples are the reference's.
+// Each ray sees exactly the reference's sample sequence (raymarching_test_kernel semantics, incl. its
+// `cascades`-as-scale quirk) and the same front-to-back accumulation order, so results differ from the
+// reference only by the fp16-level network difference (T is resumed as 1 - opacity, volumerendering.cu:230).
+// One round = THREE launches: march, network, compositing (whose last block does the next round's bookkeeping).
 #include "common.cuh"
 #include "march.cuh"
 #include "../../include/ngp_b200.h"
 #include <string.h>
 
+// per-round bookkeeping (1 thread), the head of the reference's loop (rendering.py:75-81):
+//   while samples < max_samples:  N_alive = len(alive); if N_alive == 0: break
+//       N_samples = max(min(N_rays // N_alive, 64), min_samples);  samples += N_samples
+// computed from the device-side alive count. N_alive * N_samples <= max(N_rays, min_samples * N_alive) <= 4 * N_rays, the
+// capacity of the per-round sample buffers (max_round_samples), so the quota never has to be clipped.
+// Two marching regimes (one kernel, chosen per round on the device):
+//   N_samples <  INFER_STAGE (at least N_rays/8 rays alive, few samples each) -> one THREAD per ray: one visit per empty
+//       CELL is ~5x less work than probing every chain point, and there are enough rays to fill the GPU; samples staged in
+//       shared memory and appended compactly (one atomic per warp);
+//   N_samples >= INFER_STAGE (few rays, many samples each) -> one WARP per ray (march_ray_warp: 32 chain points probed side
+//       by side), samples written straight to the ray's own N_samples slots, unused slots marked ray_idx = -1 (the network
+//       kernel skips their gathers).
+//   Measured per round at ~500 k samples (profiles/r02_infer_launches_*.md): thread-per-ray 110-146 us with the generic
+//   visit, warp-per-ray 143-208 us when applied to rounds of 2-7 samples per ray -- so the warp regime is kept for the late
+//   rounds only, and the thread-per-ray visit is specialised (no frexp/scalbn/division with one cascade, constant step).
+// state: [0] N_samples of this round (0 = loop over)  [1] `samples` so far  [2] slots the network evaluates this round
+//        [3] rounds run  [4] samples marched this round  [5] 1 = warp-per-ray regime  [6] finished-block ticket
+#define INFER_STAGE 8  // thread-per-ray regime below this many samples per ray and round (= its staging slots per thread)
+__device__ __forceinline__ void infer_begin_round(const NgpInferCfg& cfg, int* __restrict__ alive_count,
+                                                  int* __restrict__ next_count, int* __restrict__ state,
+                                                  int64_t* __restrict__ total) {
+    *total += state[4];
+    state[4] = 0;
+    state[2] = 0;
+    *next_count = 0;
+    int n_alive = *alive_count;
+    if (state[1] >= cfg.sample_budget) {
+        n_alive = 0;
+        *alive_count = 0;
+    }
+    int S = 0;
+    if (n_alive > 0) {
+        const int min_samples = cfg.exp_step_factor == 0.0f ? 1 : 4;
+        S = max(min(cfg.n_rays / n_alive, 64), min_samples);
+        const int64_t share = cfg.max_round_samples / n_alive;  // (never binds for max_round_samples >= 4 * n_rays)
+        if (share < S) S = (int)(share < 1 ? 1 : share);
+        state[1] += S;
+        state[3] += 1;
+        const bool warp_regime = S >= INFER_STAGE;
+        state[5] = warp_regime ? 1 : 0;
+        if (warp_regime) state[2] = n_alive * S;  // rectangular slots; the thread-per-ray regime counts as it appends
+    }
+    state[0] = S;
+}
+
 // init: AABB (+ near clamp), zero the accumulators. EVERY ray enters the first alive list, in order, like the reference's
 // alive_indices = arange(N_rays) (rendering.py:71): rays that miss the box take no sample in round 0 and are dropped by
 // its compositing (composite_test_fw: N_eff == 0 -> not alive), so the per-round quota N_rays // N_alive of the following
-// rounds sees the same alive counts as the reference's loop.
+// rounds sees the same alive counts as the reference's loop. Thread 0 also does the bookkeeping of round 0 (the counters
+// were cleared by the memset before this kernel).
 __global__ void k_infer_init(const NgpInferCfg cfg, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                              float* __restrict__ t_cur, float* __restrict__ t_end, float* __restrict__ opacity,
                              float* __restrict__ depth, float* __restrict__ rgb, int* __restrict__ alive,
-                             int* __restrict__ alive_count) {
+                             int* __restrict__ alive_count, int* __restrict__ next_count, int* __restrict__ state,
+                             int64_t* __restrict__ total) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r == 0) *alive_count = cfg.n_rays;
+    if (r == 0) {
+        *alive_count = cfg.n_rays;
+        infer_begin_round(cfg, alive_count, next_count, state, total);
+    }
     if (r >= cfg.n_rays) return;
     const MarchRay ray = make_march_ray(rays_o[3 * r], rays_o[3 * r + 1], rays_o[3 * r + 2],
                                         rays_d[3 * r], rays_d[3 * r + 1], rays_d[3 * r + 2]);
@@ -47,131 +96,77 @@ __global__ void k_infer_init(const NgpInferCfg cfg, const float* __restrict__ ra
     alive[r] = r;
 }
 
-// per-round bookkeeping (1 thread), the head of the reference's loop (rendering.py:75-81):
-//   while samples < max_samples:  N_alive = len(alive); if N_alive == 0: break
-//       N_samples = max(min(N_rays // N_alive, 64), min_samples);  samples += N_samples
-// computed from the device-side alive count. N_alive * N_samples <= max(N_rays, min_samples * N_alive) <= 4 * N_rays, the
-// capacity of the per-round sample buffers (max_round_samples), so the quota never has to be clipped.
-// Two marching regimes (both kernels are launched every round, the one whose regime it is not exits at once):
-//   more than half of the rays alive (the first round(s): every ray walks from the box entry to its first samples, and
-//       one visit per empty CELL is ~5x less work than probing every chain point) -> one THREAD per ray, samples staged
-//       in shared memory and appended compactly (one atomic per warp);
-//   otherwise -> one WARP per ray (march_ray_warp: 32 chain points probed side by side; no lane waits for a neighbour
-//       that still walks through empty space, which is what made the thread-per-ray kernel 110-150 us per round at 2-7
-//       samples per ray, profiles/r02_infer_launches_before.md), samples written straight to the ray's own N_samples slots,
-//       unused slots marked ray_idx = -1 (the network kernel skips their gathers).
-// state: [0] N_samples of this round (0 = loop over)  [1] `samples` so far  [2] slots the network evaluates this round
-//        [3] rounds run  [4] samples marched this round  [5] 1 = warp-per-ray regime
-#define INFER_STAGE 4  // staging slots per thread in the thread-per-ray regime (N_samples <= max(1, min_samples) = 4 there)
-__global__ void k_infer_round_begin(const NgpInferCfg cfg, int* __restrict__ alive_count, int* __restrict__ next_count,
-                                    int* __restrict__ state, int64_t* __restrict__ total) {
-    *total += state[4];
-    state[4] = 0;
-    state[2] = 0;
-    *next_count = 0;
-    int n_alive = *alive_count;
-    if (state[1] >= cfg.sample_budget) {
-        n_alive = 0;
-        *alive_count = 0;
-    }
-    int S = 0;
-    if (n_alive > 0) {
-        const int min_samples = cfg.exp_step_factor == 0.0f ? 1 : 4;
-        S = max(min(cfg.n_rays / n_alive, 64), min_samples);
-        const int64_t share = cfg.max_round_samples / n_alive;  // (never binds for max_round_samples >= 4 * n_rays)
-        if (share < S) S = (int)(share < 1 ? 1 : share);
-        state[1] += S;
-        state[3] += 1;
-        const bool warp_regime = 2 * (int64_t)n_alive <= cfg.n_rays || S > INFER_STAGE;
-        state[5] = warp_regime ? 1 : 0;
-        if (warp_regime) state[2] = n_alive * S;  // rectangular slots; the thread-per-ray regime counts as it appends
-    }
-    state[0] = S;
-}
-
-// one round of marching, thread-per-ray regime: every alive ray takes up to S <= INFER_STAGE occupied samples (staged in
-// shared memory), then the warp claims a contiguous range of the compact sample arrays with one atomic.
-#define INFER_A_THREADS 128
+// one round of marching; the regime (state[5]) is uniform over the grid
+#define INFER_THREADS 128
 template <bool CONST_DT, bool ONE_CASCADE>
-__global__ void __launch_bounds__(INFER_A_THREADS)
+__global__ void __launch_bounds__(INFER_THREADS)
 k_infer_march(const NgpInferCfg cfg, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
               const uint8_t* __restrict__ bitfield, float* __restrict__ t_cur, const float* __restrict__ t_end,
               const int* __restrict__ alive, const int* __restrict__ alive_count, int* __restrict__ ray_start,
               int* __restrict__ ray_n, int* __restrict__ ray_idx, float* __restrict__ ts, float* __restrict__ deltas,
               int* __restrict__ state) {
-    __shared__ float2 stage[INFER_A_THREADS][INFER_STAGE];
+    __shared__ float2 stage[INFER_THREADS][INFER_STAGE - 1];
     const int S = state[0];
-    if (S <= 0 || state[5]) return;
+    if (S <= 0) return;
     const int lane = threadIdx.x & 31;
     const int n_alive = *alive_count;
     const MarchConst c = make_march_const(bitfield, cfg.cascades, cfg.grid_size, cfg.max_samples, cfg.scale, cfg.exp_step_factor,
                                           (float)cfg.cascades);
-    // whole warps stride over the alive list (a warp's 32 rays append with one atomic)
-    const int n_pad = (n_alive + 31) & ~31;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) {
-        float2* my = stage[threadIdx.x];
-        int n = 0, r = -1;
-        float t = 0.f;
-        if (i < n_alive) {
-            r = alive[i];
-            const MarchRay ray = make_march_ray(rays_o[3 * r], rays_o[3 * r + 1], rays_o[3 * r + 2],
-                                                rays_d[3 * r], rays_d[3 * r + 1], rays_d[3 * r + 2]);
-            t = t_cur[r];
-            const float t2 = t_end[r];
-            float dt;
-            while (t < t2 && n < S) {
-                if (march_visit_t<CONST_DT, ONE_CASCADE>(ray, c, t, dt)) {
-                    my[n] = make_float2(t, dt);
-                    t = __fadd_rn(t, dt);
-                    ++n;
+    if (!state[5]) {
+        // ---- thread per ray: up to S < INFER_STAGE occupied samples per ray, staged, then one atomic per warp claims a
+        //      contiguous range of the compact sample arrays; whole warps stride over the alive list ----
+        const int n_pad = (n_alive + 31) & ~31;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) {
+            float2* my = stage[threadIdx.x];
+            int n = 0, r = -1;
+            float t = 0.f;
+            if (i < n_alive) {
+                r = alive[i];
+                const MarchRay ray = make_march_ray(rays_o[3 * r], rays_o[3 * r + 1], rays_o[3 * r + 2],
+                                                    rays_d[3 * r], rays_d[3 * r + 1], rays_d[3 * r + 2]);
+                t = t_cur[r];
+                const float t2 = t_end[r];
+                float dt;
+                uint32_t cache_idx = 0xffffffffu;
+                bool cache_occ = false;
+                while (t < t2 && n < S) {
+                    if (march_visit_cached<CONST_DT, ONE_CASCADE>(ray, c, t, dt, cache_idx, cache_occ)) {
+                        my[n] = make_float2(t, dt);
+                        t = __fadd_rn(t, dt);
+                        ++n;
+                    }
                 }
             }
-        }
-        // inclusive prefix of the counts across the warp, one atomic per warp
-        int pre = n;
+            int pre = n;  // inclusive prefix of the counts across the warp
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int u = __shfl_up_sync(0xffffffffu, pre, o);
-            if (lane >= o) pre += u;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, pre, o);
+                if (lane >= o) pre += u;
+            }
+            const int warp_total = __shfl_sync(0xffffffffu, pre, 31);
+            int base = 0;
+            if (lane == 31 && warp_total > 0) {
+                base = atomicAdd(&state[2], warp_total);
+                atomicAdd(&state[4], warp_total);
+            }
+            base = __shfl_sync(0xffffffffu, base, 31);
+            if (r < 0) continue;
+            const int start = base + pre - n;  // n_alive * S <= capacity, so this always fits
+            ray_start[i] = start;
+            ray_n[i] = n;
+            t_cur[r] = t;
+            for (int k = 0; k < n; ++k) {
+                ray_idx[start + k] = r;
+                ts[start + k] = my[k].x;
+                deltas[start + k] = my[k].y;
+            }
         }
-        const int warp_total = __shfl_sync(0xffffffffu, pre, 31);
-        int base = 0;
-        if (lane == 31 && warp_total > 0) {
-            base = atomicAdd(&state[2], warp_total);
-            atomicAdd(&state[4], warp_total);
-        }
-        base = __shfl_sync(0xffffffffu, base, 31);
-        if (r < 0) continue;
-        const int start = base + pre - n;  // n_alive * S <= capacity, so this always fits
-        ray_start[i] = start;
-        ray_n[i] = n;
-        t_cur[r] = t;
-        for (int k = 0; k < n; ++k) {
-            ray_idx[start + k] = r;
-            ts[start + k] = my[k].x;
-            deltas[start + k] = my[k].y;
-        }
+        return;
     }
-}
-
-// warp-per-ray regime: same sample sequence, 32 chain points probed at a time (march_ray_warp); ray i owns slots
-// [i*S, (i+1)*S). The next ray's index, origin, direction and interval are fetched while the current one is marched.
-template <bool CONST_DT, bool ONE_CASCADE>
-__global__ void __launch_bounds__(128)
-k_infer_march_warp(const NgpInferCfg cfg, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-                   const uint8_t* __restrict__ bitfield, float* __restrict__ t_cur, const float* __restrict__ t_end,
-                   const int* __restrict__ alive, const int* __restrict__ alive_count, int* __restrict__ ray_start,
-                   int* __restrict__ ray_n, int* __restrict__ ray_idx, float* __restrict__ ts, float* __restrict__ deltas,
-                   int* __restrict__ state) {
-    const int S = state[0];
-    if (S <= 0 || !state[5]) return;
-    const int lane = threadIdx.x & 31;
-    const int n_alive = *alive_count;
-    const MarchConst c = make_march_const(bitfield, cfg.cascades, cfg.grid_size, cfg.max_samples, cfg.scale, cfg.exp_step_factor,
-                                          (float)cfg.cascades);
+    // ---- warp per ray: same sample sequence, 32 chain points probed at a time (march_ray_warp); ray i owns slots
+    //      [i*S, (i+1)*S). Lanes 0..7 hold {ox,oy,oz,dx,dy,dz,t,t2} of the NEXT ray (one load each) while this one is marched ----
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     int marched = 0;
-    // lanes 0..7 of the warp hold {ox,oy,oz,dx,dy,dz,t,t2} of the NEXT ray (one load each), broadcast when its turn comes
     int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int r_next = i < n_alive ? alive[i] : -1;
     auto fetch = [&](int r) -> float {
@@ -210,16 +205,18 @@ k_infer_march_warp(const NgpInferCfg cfg, const float* __restrict__ rays_o, cons
     if (lane == 0 && marched) atomicAdd(&state[4], marched);
 }
 
-// composite this round's samples of every alive ray (one thread per ray, <= 64 samples, same serial
-// order as the reference's composite_test_fw_kernel) and append the survivors to the next alive list
+// composite this round's samples of every alive ray (one thread per ray, <= 64 samples, same serial order as the
+// reference's composite_test_fw_kernel) and append the survivors to the next alive list. The LAST block to finish does the
+// next round's bookkeeping (infer_begin_round on the swapped lists) and, inside the frame graph, sets the WHILE node's
+// condition (`handle` != 0 on the second round of the loop body).
 __global__ void k_infer_composite(const NgpInferCfg cfg, const float* __restrict__ sigmas,
                                   const float* __restrict__ rgbs, const float* __restrict__ deltas,
                                   const float* __restrict__ ts, const int* __restrict__ ray_start,
-                                  const int* __restrict__ ray_n, const float* __restrict__ t_cur,
-                                  const float* __restrict__ t_end, const int* __restrict__ alive,
-                                  const int* __restrict__ alive_count, float* __restrict__ opacity,
+                                  const int* __restrict__ ray_n, const int* __restrict__ alive,
+                                  int* __restrict__ alive_count, float* __restrict__ opacity,
                                   float* __restrict__ depth, float* __restrict__ rgb, int* __restrict__ next_alive,
-                                  int* __restrict__ next_count) {
+                                  int* __restrict__ next_count, int* __restrict__ state, int64_t* __restrict__ total,
+                                  const cudaGraphConditionalHandle handle, const int set_cond) {
     const int lane = threadIdx.x & 31;
     const int n_alive = *alive_count;
     const int n_pad = (n_alive + 31) & ~31;
@@ -266,6 +263,15 @@ __global__ void k_infer_composite(const NgpInferCfg cfg, const float* __restrict
             if (keep) next_alive[base + __popc(m & ((1u << lane) - 1u))] = r;
         }
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&state[6], 1) == (int)gridDim.x - 1) {  // every block's appends are visible
+            state[6] = 0;
+            infer_begin_round(cfg, next_count, alive_count, state, total);  // the lists swap roles
+            if (set_cond) cudaGraphSetConditional(handle, state[0] > 0 ? 1u : 0u);
+        }
+    }
 }
 
 __global__ void k_infer_finish(const NgpInferCfg cfg, const float* __restrict__ opacity, float* __restrict__ rgb,
@@ -278,7 +284,6 @@ __global__ void k_infer_finish(const NgpInferCfg cfg, const float* __restrict__ 
     rgb[3 * r + 1] += cfg.bg[1] * rest;
     rgb[3 * r + 2] += cfg.bg[2] * rest;
 }
-
 
 struct InferWs {
     float *t_cur, *t_end;
@@ -313,7 +318,8 @@ static InferWs infer_ws(const NgpInferCfg* cfg, void* workspace) {
 
 // one round of the wavefront on stream st; the ping-pong role of the two alive lists is given by `cur`
 static int infer_round(const NgpNet* net, const NgpInferCfg* cfg, const InferWs& W, const float* rays_o, const float* rays_d,
-                       const uint8_t* density_bitfield, float* opacity, float* depth, float* rgb, int cur, cudaStream_t st);
+                       const uint8_t* density_bitfield, float* opacity, float* depth, float* rgb, int cur, cudaStream_t st,
+                       cudaGraphConditionalHandle handle = 0, int set_cond = 0);
 
 extern "C" size_t ngp_render_infer_workspace(int n_rays, int64_t max_round_samples) {
     if (n_rays < 1 || max_round_samples < 1) return 0;
@@ -349,7 +355,7 @@ extern "C" int ngp_render_infer(const NgpNet* net, const NgpInferCfg* cfg, const
         NGP_CUDA(cudaMemsetAsync(W.counters, 0, 4096, st));
         NGP_COUNT_LAUNCHES(1);
         k_infer_init<<<ngp_div_up(n, 256), 256, 0, st>>>(*cfg, rays_o, rays_d, W.t_cur, W.t_end, opacity, depth, rgb, W.alive[0],
-                                                          alive_cnt);
+                                                          alive_cnt, alive_cnt + 1, W.state, W.total);
         NGP_CHECK_LAUNCH();
     }
     for (int round = first_round; round < first_round + n_rounds; ++round) {
@@ -367,63 +373,47 @@ extern "C" int ngp_render_infer(const NgpNet* net, const NgpInferCfg* cfg, const
 }
 
 static int infer_round(const NgpNet* net, const NgpInferCfg* cfg, const InferWs& W, const float* rays_o, const float* rays_d,
-                       const uint8_t* density_bitfield, float* opacity, float* depth, float* rgb, int cur, cudaStream_t st) {
+                       const uint8_t* density_bitfield, float* opacity, float* depth, float* rgb, int cur, cudaStream_t st,
+                       cudaGraphConditionalHandle handle, int set_cond) {
     const int n = cfg->n_rays;
     const int nxt = cur ^ 1;
     // persistent-style grids (the kernels stride over the device-side alive count): enough blocks to fill the GPU, never
     // tens of thousands of blocks that find nothing to do in the late rounds
     const int sms = ngp_sm_count();
-    const int grid_a = (int)min((int64_t)ngp_div_up(n, INFER_A_THREADS), (int64_t)sms * 16);
-    const int grid_w = (int)min((int64_t)ngp_div_up((int64_t)(n / 2 + 1) * 32, 128), (int64_t)sms * 16);
+    const int grid_m = (int)min((int64_t)ngp_div_up(n, INFER_THREADS), (int64_t)sms * 16);
     const int grid_c = (int)min((int64_t)ngp_div_up(n, 128), (int64_t)sms * 16);
-    k_infer_round_begin<<<1, 1, 0, st>>>(*cfg, W.alive_cnt + cur, W.alive_cnt + nxt, W.state, W.total);
-    NGP_CHECK_LAUNCH();
     // the test-time step bounds use `cascades` where the train kernel uses `scale` (reference raymarching.cu:370,399)
     const bool const_dt = cfg->exp_step_factor == 0.0f &&
                           1.73205080757f / (float)cfg->max_samples <= (float)cfg->cascades * 3.46410161514f / (float)cfg->grid_size;
-#define NGP_LAUNCH_IA(CD, OC)                                                                                                  \
-    k_infer_march<CD, OC><<<grid_a, INFER_A_THREADS, 0, st>>>(*cfg, rays_o, rays_d, density_bitfield, W.t_cur, W.t_end,        \
-                                                              W.alive[cur], W.alive_cnt + cur, W.ray_start, W.ray_n, W.ray_idx, \
-                                                              W.ts, W.deltas, W.state)
-    if (const_dt && cfg->cascades == 1) NGP_LAUNCH_IA(true, true);
-    else if (const_dt) NGP_LAUNCH_IA(true, false);
-    else if (cfg->cascades == 1) NGP_LAUNCH_IA(false, true);
-    else NGP_LAUNCH_IA(false, false);
-#undef NGP_LAUNCH_IA
-    NGP_CHECK_LAUNCH();
-#define NGP_LAUNCH_IW(CD, OC)                                                                                                  \
-    k_infer_march_warp<CD, OC><<<grid_w, 128, 0, st>>>(*cfg, rays_o, rays_d, density_bitfield, W.t_cur, W.t_end, W.alive[cur], \
-                                                       W.alive_cnt + cur, W.ray_start, W.ray_n, W.ray_idx, W.ts, W.deltas, W.state)
-    if (const_dt && cfg->cascades == 1) NGP_LAUNCH_IW(true, true);
-    else if (const_dt) NGP_LAUNCH_IW(true, false);
-    else if (cfg->cascades == 1) NGP_LAUNCH_IW(false, true);
-    else NGP_LAUNCH_IW(false, false);
-#undef NGP_LAUNCH_IW
+#define NGP_LAUNCH_IM(CD, OC)                                                                                              \
+    k_infer_march<CD, OC><<<grid_m, INFER_THREADS, 0, st>>>(*cfg, rays_o, rays_d, density_bitfield, W.t_cur, W.t_end,      \
+                                                            W.alive[cur], W.alive_cnt + cur, W.ray_start, W.ray_n, W.ray_idx, \
+                                                            W.ts, W.deltas, W.state)
+    if (const_dt && cfg->cascades == 1) NGP_LAUNCH_IM(true, true);
+    else if (const_dt) NGP_LAUNCH_IM(true, false);
+    else if (cfg->cascades == 1) NGP_LAUNCH_IM(false, true);
+    else NGP_LAUNCH_IM(false, false);
+#undef NGP_LAUNCH_IM
     NGP_CHECK_LAUNCH();
     NgpSamples smp;
     smp.xyzs = nullptr; smp.dirs = nullptr; smp.rays_o = rays_o; smp.rays_d = rays_d; smp.ray_idx = W.ray_idx; smp.ts = W.ts;
     smp.n = cfg->max_round_samples; smp.n_dev = W.state + 2; smp.live_idx = nullptr; smp.n_live_dev = nullptr;
     int rc = ngp_net_forward(net, &smp, 1, W.sigmas, W.rgbs, nullptr, nullptr, (void*)st);
     if (rc) return rc;
-    k_infer_composite<<<grid_c, 128, 0, st>>>(*cfg, W.sigmas, W.rgbs, W.deltas, W.ts, W.ray_start, W.ray_n, W.t_cur, W.t_end,
-                                               W.alive[cur], W.alive_cnt + cur, opacity, depth, rgb, W.alive[nxt], W.alive_cnt + nxt);
+    k_infer_composite<<<grid_c, 128, 0, st>>>(*cfg, W.sigmas, W.rgbs, W.deltas, W.ts, W.ray_start, W.ray_n, W.alive[cur],
+                                               W.alive_cnt + cur, opacity, depth, rgb, W.alive[nxt], W.alive_cnt + nxt, W.state,
+                                               W.total, handle, set_cond);
     NGP_CHECK_LAUNCH();
     return 0;
 }
 
 // -------------------------------------------------------------------------------------------------
 // The whole frame as ONE CUDA graph with a device-side loop: init -> WHILE(alive rays left and sample budget not used up)
-// { two rounds (the alive lists ping-pong) } -> finish. The loop is a conditional WHILE node whose condition a 1-thread
-// kernel at the end of the body sets from the device-side alive count (cudaGraphSetConditional), so the host enqueues one
+// { two rounds (the alive lists ping-pong) } -> finish. The loop is a conditional WHILE node whose condition the last block
+// of the second round's compositing kernel sets (cudaGraphSetConditional: another round is due), so the host enqueues one
 // graph launch per frame and never reads anything back. The instantiated graph is cached per (device, arguments): a
 // caller that renders frame after frame from the same buffers pays the build once.
 // -------------------------------------------------------------------------------------------------
-__global__ void k_infer_loop_cond(const NgpInferCfg cfg, const int* __restrict__ alive_count, const int* __restrict__ state,
-                                  cudaGraphConditionalHandle handle) {
-    // next iteration iff rays are left and the reference's loop condition `samples < max_samples` still holds
-    cudaGraphSetConditional(handle, (*alive_count > 0 && state[1] < cfg.sample_budget) ? 1u : 0u);
-}
-
 struct InferGraphKey {
     NgpNet net;
     NgpInferCfg cfg;
@@ -461,7 +451,7 @@ static int build_infer_graph(const InferGraphKey& k, InferGraphEntry* e) {
         if ((rc = (int)cudaStreamBeginCaptureToGraph(cs, g, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal))) break;
         cudaMemsetAsync(W.counters, 0, 4096, cs);
         k_infer_init<<<ngp_div_up(n, 256), 256, 0, cs>>>(*cfg, rays_o, rays_d, W.t_cur, W.t_end, opacity, depth, rgb, W.alive[0],
-                                                          W.alive_cnt);
+                                                          W.alive_cnt, W.alive_cnt + 1, W.state, W.total);
         cudaStreamCaptureStatus status;
         const cudaGraphNode_t* deps = nullptr;
         size_t n_deps = 0;
@@ -483,9 +473,8 @@ static int build_infer_graph(const InferGraphKey& k, InferGraphEntry* e) {
         if ((rc = (int)cudaGraphAddNode(&loop, g, head_tail, n_deps, &cp))) break;
         cudaGraph_t body = cp.conditional.phGraph_out[0];
         if ((rc = (int)cudaStreamBeginCaptureToGraph(cs, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal))) break;
-        for (int half = 0; half < 2 && !rc; ++half)
-            rc = infer_round(net, cfg, W, rays_o, rays_d, bitfield, opacity, depth, rgb, half, cs);
-        k_infer_loop_cond<<<1, 1, 0, cs>>>(*cfg, W.alive_cnt + 0, W.state, handle);  // after two rounds list 0 is current again
+        for (int half = 0; half < 2 && !rc; ++half)  // the second round's compositing sets the loop condition
+            rc = infer_round(net, cfg, W, rays_o, rays_d, bitfield, opacity, depth, rgb, half, cs, handle, half);
         int rc2 = (int)cudaStreamEndCapture(cs, &tmp);
         if (rc) break;
         if ((rc = rc2)) break;

@@ -6,7 +6,6 @@
 #include "march.cuh"
 #include "composite.cuh"
 #include "../../include/ngp_b200.h"
-#include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
 
@@ -19,57 +18,65 @@ static inline int one_thread_per_ray_block(int n_rays) { return n_rays >= 148 * 
 template <bool CONST_DT, bool ONE_CASCADE>
 __global__ void k_train_march(const NgpTrainCfg cfg, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                               const float* __restrict__ noise, const uint8_t* __restrict__ bitfield,
-                              float* __restrict__ stage_t, float* __restrict__ stage_dt, int* __restrict__ n_samples) {
+                              float* __restrict__ stage_t, float* __restrict__ stage_dt, int* __restrict__ n_samples,
+                              int* __restrict__ offsets, int* __restrict__ ray_idx, float* __restrict__ ts,
+                              float* __restrict__ deltas, int* __restrict__ counters, int* __restrict__ acc) {
     // one WARP per ray (march_ray_warp): 32 chain points probed side by side, same t sequence as the serial loop
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (r >= cfg.n_rays) return;
-    const MarchConst c = make_march_const(bitfield, cfg.cascades, cfg.grid_size, cfg.max_samples, cfg.scale,
-                                          cfg.exp_step_factor, cfg.scale);
-    const MarchRay ray = make_march_ray(rays_o[3 * r], rays_o[3 * r + 1], rays_o[3 * r + 2],
-                                        rays_d[3 * r], rays_d[3 * r + 1], rays_d[3 * r + 2]);
-    const float2 tt = ray_aabb(ray, cfg.center[0], cfg.center[1], cfg.center[2], cfg.half_size[0], cfg.half_size[1],
-                               cfg.half_size[2]);
-    float t1 = -1.0f, t2 = -1.0f;
-    if (tt.y > 0.0f) {
-        t1 = fmaxf(tt.x, 0.0f);
-        t2 = tt.y;
+    if (r < cfg.n_rays) {
+        const MarchConst c = make_march_const(bitfield, cfg.cascades, cfg.grid_size, cfg.max_samples, cfg.scale,
+                                              cfg.exp_step_factor, cfg.scale);
+        const MarchRay ray = make_march_ray(rays_o[3 * r], rays_o[3 * r + 1], rays_o[3 * r + 2],
+                                            rays_d[3 * r], rays_d[3 * r + 1], rays_d[3 * r + 2]);
+        const float2 tt = ray_aabb(ray, cfg.center[0], cfg.center[1], cfg.center[2], cfg.half_size[0], cfg.half_size[1],
+                                   cfg.half_size[2]);
+        float t1 = -1.0f, t2 = -1.0f;
+        if (tt.y > 0.0f) {
+            t1 = fmaxf(tt.x, 0.0f);
+            t2 = tt.y;
+        }
+        if (t1 >= 0.0f && t1 < cfg.near_distance) t1 = cfg.near_distance;
+        const float t = march_jitter(t1, noise[r], c);
+        float* st = stage_t + (size_t)r * cfg.max_samples;
+        float* sd = stage_dt + (size_t)r * cfg.max_samples;
+        const int n = march_ray_warp<CONST_DT, ONE_CASCADE>(ray, c, t, t2, cfg.max_samples, lane, [&](int k, float ts_, float dts) {
+            st[k] = ts_;
+            sd[k] = dts;
+        });
+        // The ray's segment of the compact per-sample arrays: claimed with one atomic, in arrival order like the reference's
+        // rays_a (raymarching.cu:237-241) -- every consumer goes through offsets[ray] / n_samples[ray], none needs the
+        // segments sorted by ray. Replaces a prefix-sum kernel and a compaction kernel; the staging row just written by this
+        // warp is still in L1/L2 when it is copied out.
+        int start = 0;
+        if (lane == 0) {
+            start = atomicAdd(&acc[0], n);
+            n_samples[r] = n;
+            offsets[r] = start;
+        }
+        start = __shfl_sync(0xffffffffu, start, 0);
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) {
+            const int64_t s = (int64_t)start + i;
+            if (s < cfg.max_total_samples) {
+                ray_idx[s] = r;
+                ts[s] = st[i];
+                deltas[s] = sd[i];
+            }
+        }
     }
-    if (t1 >= 0.0f && t1 < cfg.near_distance) t1 = cfg.near_distance;
-    const float t = march_jitter(t1, noise[r], c);
-    float* st = stage_t + (size_t)r * cfg.max_samples;
-    float* sd = stage_dt + (size_t)r * cfg.max_samples;
-    const int n = march_ray_warp<CONST_DT, ONE_CASCADE>(ray, c, t, t2, cfg.max_samples, lane, [&](int k, float ts, float dts) {
-        st[k] = ts;
-        sd[k] = dts;
-    });
-    if (lane == 0) n_samples[r] = n;
-}
-
-// 3. staging rows -> compact per-sample arrays (one warp per ray, coalesced both ways)
-__global__ void k_train_compact(const NgpTrainCfg cfg, const float* __restrict__ stage_t, const float* __restrict__ stage_dt,
-                                const int* __restrict__ n_samples, const int* __restrict__ offsets,
-                                int* __restrict__ ray_idx, float* __restrict__ ts, float* __restrict__ deltas,
-                                int* __restrict__ counters) {
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (w >= cfg.n_rays) return;
-    const int n = n_samples[w];
-    const int64_t start = offsets[w];
-    if (w == cfg.n_rays - 1 && lane == 0) {
-        int64_t tot = start + n;
-        counters[0] = (int)(tot < cfg.max_total_samples ? tot : cfg.max_total_samples);
-        counters[1] = 0;
-        counters[4] = 0;
-    }
-    const float* st = stage_t + (size_t)w * cfg.max_samples;
-    const float* sd = stage_dt + (size_t)w * cfg.max_samples;
-    for (int i = lane; i < n; i += 32) {
-        const int64_t s = start + i;
-        if (s < cfg.max_total_samples) {
-            ray_idx[s] = w;
-            ts[s] = st[i];
-            deltas[s] = sd[i];
+    // the last block to finish publishes the total and re-arms the accumulators (the network kernels read counters[0];
+    // a trainer may already be marching the NEXT batch into another buffer set, with its own counters and accumulators)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&acc[1], 1) == (int)gridDim.x - 1) {
+            const int tot = atomicAdd(&acc[0], 0);
+            counters[0] = (int)((int64_t)tot < cfg.max_total_samples ? tot : cfg.max_total_samples);
+            counters[1] = 0;
+            counters[4] = 0;
+            acc[0] = 0;
+            acc[1] = 0;
         }
     }
 }
@@ -109,9 +116,8 @@ __global__ void k_train_composite_fw(const NgpTrainCfg cfg, const int* __restric
 }
 
 extern "C" size_t ngp_train_scan_temp_bytes(int n_rays) {
-    size_t bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const int*)nullptr, (int*)nullptr, n_rays > 0 ? n_rays : 1);
-    return (bytes + 255) & ~(size_t)255;
+    (void)n_rays;
+    return 256;  // two int32 accumulators of the march kernel's segment allocation (zero-initialised ONCE by the caller)
 }
 
 static NgpSamples train_samples(const NgpTrainCfg* cfg, const NgpTrainBuffers* b) {
@@ -138,31 +144,7 @@ static int check_train_args(const NgpNet* net, const NgpTrainCfg* cfg, const Ngp
     return 0;
 }
 
-// exclusive prefix sum of up to 1024*SCAN1_ITEMS per-ray counts by ONE block (the training batch is 8192 rays: a
-// device-wide scan would cost two launches for 32 KB of data)
-#define SCAN1_ITEMS 16
-__global__ void __launch_bounds__(1024) k_scan_one_block(const int* __restrict__ in, int* __restrict__ out, int n) {
-    typedef cub::BlockScan<int, 1024> BlockScan;
-    __shared__ typename BlockScan::TempStorage temp;
-    const int per = (n + 1023) / 1024;  // <= SCAN1_ITEMS consecutive items per thread
-    const int first = threadIdx.x * per;
-    int v[SCAN1_ITEMS];
-    int sum = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN1_ITEMS; ++k) {
-        v[k] = (k < per && first + k < n) ? in[first + k] : 0;
-        sum += v[k];
-    }
-    int base;
-    BlockScan(temp).ExclusiveSum(sum, base);
-#pragma unroll
-    for (int k = 0; k < SCAN1_ITEMS; ++k) {
-        if (k < per && first + k < n) out[first + k] = base;
-        base += v[k];
-    }
-}
-
-// first half of the forward: AABB + march + prefix sum + compaction. Depends only on the rays, the jitter
+// first half of the forward: AABB + march + segment allocation + compaction in ONE kernel. Depends only on the rays, the jitter
 // and the occupancy bitfield (NOT on the network weights), so a trainer may run it for step i+1 while the
 // optimiser of step i is still updating the weights.
 extern "C" int ngp_render_train_march(const NgpTrainCfg* cfg, const NgpTrainBuffers* b, void* stream) {
@@ -175,25 +157,18 @@ extern "C" int ngp_render_train_march(const NgpTrainCfg* cfg, const NgpTrainBuff
     const bool const_dt = cfg->exp_step_factor == 0.0f &&
                           1.73205080757f / (float)cfg->max_samples <= cfg->scale * 3.46410161514f / (float)cfg->grid_size;
     const dim3 mg(ngp_div_up((int64_t)n * 32, 128));
+    // accumulators of the march kernel's segment allocation: two ints at the head of scan_temp, zero between launches
+    // (zeroed once by the caller -- torch allocates scan_temp zero-filled in the Trainer -- and re-armed by the kernel)
+    int* acc = (int*)b->scan_temp;
 #define NGP_LAUNCH_MARCH(CD, OC)                                                                                        \
     k_train_march<CD, OC><<<mg, 128, 0, st>>>(*cfg, b->rays_o, b->rays_d, b->noise, b->density_bitfield, b->stage_t, \
-                                              b->stage_dt, b->n_samples)
+                                              b->stage_dt, b->n_samples, b->offsets, b->ray_idx, b->ts, b->deltas,    \
+                                              b->counters, acc)
     if (const_dt && cfg->cascades == 1) NGP_LAUNCH_MARCH(true, true);
     else if (const_dt) NGP_LAUNCH_MARCH(true, false);
     else if (cfg->cascades == 1) NGP_LAUNCH_MARCH(false, true);
     else NGP_LAUNCH_MARCH(false, false);
 #undef NGP_LAUNCH_MARCH
-    NGP_CHECK_LAUNCH();
-    if (n <= 1024 * SCAN1_ITEMS) {
-        k_scan_one_block<<<1, 1024, 0, st>>>(b->n_samples, b->offsets, n);
-        NGP_CHECK_LAUNCH();
-    } else {
-        size_t temp_bytes = b->scan_temp_bytes;
-        NGP_CUDA(cub::DeviceScan::ExclusiveSum(b->scan_temp, temp_bytes, b->n_samples, b->offsets, n, st));
-        NGP_COUNT_LAUNCHES(2);  // cub: init + sweep kernels
-    }
-    k_train_compact<<<ngp_div_up((int64_t)n * 32, 256), 256, 0, st>>>(*cfg, b->stage_t, b->stage_dt, b->n_samples, b->offsets,
-                                                                       b->ray_idx, b->ts, b->deltas, b->counters);
     NGP_CHECK_LAUNCH();
     return 0;
 }

@@ -275,7 +275,7 @@ class Trainer:
                 self.wts_inc = torch.empty(cap, **f32)
                 self.dL_dws = torch.zeros(cap, **f32)
             scan_bytes = L.ngp_train_scan_temp_bytes(N)
-            self.scan_temp = torch.empty(scan_bytes, device=dev, dtype=torch.uint8)
+            self.scan_temp = torch.zeros(scan_bytes, device=dev, dtype=torch.uint8)  # march accumulators: zero once
             bwd_bytes = L.ngp_net_backward_workspace(cap)
             self.bwd_ws = torch.empty(bwd_bytes, device=dev, dtype=torch.uint8)
             for st_ in self._sets:

@@ -62,10 +62,14 @@ def test_fused_train_step_matches_unfused_autograd(which):
     assert int(res["vr_samples"]) == st["vr_samples"]
     assert torch.equal(res["rays_a"][:, 2].int(), tr.n_samples)
     tot = st["rm_samples"]
-    assert torch.equal(res["ts"], tr.ts[:tot]) and torch.equal(res["deltas"], tr.deltas[:tot])
+    # the fused path allocates a ray's segment in arrival order (like the reference's atomic rays_a), the operator path in
+    # ray order: sample i of the operator path lives in slot[i] of the fused path's arrays
+    ra = res["rays_a"]
+    slot = torch.repeat_interleave(tr.offsets.long() - ra[:, 1], ra[:, 2]) + torch.arange(tot, device="cuda")
+    assert torch.equal(res["ts"], tr.ts[slot]) and torch.equal(res["deltas"], tr.deltas[slot])
     for k, mine in (("rgb", tr.rgb), ("opacity", tr.opacity), ("depth", tr.depth)):
         assert torch.allclose(res[k].float(), mine, rtol=1e-5, atol=1e-6), k
-    assert torch.allclose(res["ws"], tr.ws[:tot], rtol=1e-5, atol=1e-7)
+    assert torch.allclose(res["ws"], tr.ws[slot], rtol=1e-5, atol=1e-7)
     # reference NeRFLoss (losses.py:47-60, no distortion) in torch
     op = res["opacity"] + 1e-10
     loss = ((res["rgb"] - gt) ** 2).mean() + (1e-3 * (-op * torch.log(op))).mean()
@@ -292,9 +296,17 @@ def test_warp_marcher_bit_exact_vs_oracle(name, oracle):
     assert (tr.n_samples.cpu().numpy() == ra[:, 2]).all()
     tot = int(ra[:, 2].sum())
     assert int(tr.counters[0]) == tot
-    assert (tr.ts[:tot].cpu().numpy().view(np.uint32) == ts.view(np.uint32)).all()
-    assert (tr.deltas[:tot].cpu().numpy().view(np.uint32) == deltas.view(np.uint32)).all()
-    assert (tr.ray_idx[:tot].cpu().numpy() == np.repeat(np.arange(n), ra[:, 2])).all()
+    # the fused path hands every ray a segment of the compact arrays in arrival order (like the reference's atomic rays_a);
+    # the segments partition [0, total) and each holds exactly the oracle's samples of its ray, bit for bit
+    off = tr.offsets.cpu().numpy().astype(np.int64)
+    cnt = ra[:, 2].astype(np.int64)
+    order = np.argsort(off, kind="stable")
+    nz = order[cnt[order] > 0]
+    assert (off[nz] == np.concatenate([[0], np.cumsum(cnt[nz])[:-1]])).all()
+    gather = (np.repeat(off - ra[:, 1], cnt) + np.arange(tot)).astype(np.int64)  # oracle sample i (ray order) -> its slot
+    assert (tr.ts.cpu().numpy()[gather].view(np.uint32) == ts.view(np.uint32)).all()
+    assert (tr.deltas.cpu().numpy()[gather].view(np.uint32) == deltas.view(np.uint32)).all()
+    assert (tr.ray_idx.cpu().numpy()[gather] == np.repeat(np.arange(n), cnt)).all()
 
 
 def test_fused_nvlink_optimizer_step_two_gpus(tmp_path):

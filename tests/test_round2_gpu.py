@@ -115,13 +115,13 @@ def test_outside_parameter_writes_reach_the_kernels():
     want = other.density(x)
     before = model.density(x)
     assert not torch.allclose(before, want)
-    model.load_state_dict(other.state_dict())
+    model.load_state_dict(other.state_dict(), strict=False)  # (`other` has no density_grid buffer: only a Trainer registers one)
     assert torch.equal(model.density(x), want)
     with torch.no_grad():
         model.xyz_encoder.params.data.mul_(0.5)
     tr.sync_params()
     half = NGP(scene.scale).cuda()
-    half.load_state_dict(model.state_dict())
+    half.load_state_dict(model.state_dict(), strict=False)
     assert torch.equal(model.density(x), half.density(x))
     # stand-alone module (no Trainer): a write through .data must be seen by the next training forward
     m2 = make_model(scene, seed=7)
