@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "hashgrid.cuh"
 #include "mlp.cuh"
+#include "umma.cuh"
 #include "../../include/ngp_b200.h"
 #include <math.h>
 #include <stdlib.h>
@@ -978,6 +979,346 @@ k_ngp_bwd2(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_
 }
 
 // -------------------------------------------------------------------------------------------------
+// backward, tcgen05 variant (default): the dgrad chain stays on mma.sync fragments in the sixteen warps, but the five
+// WEIGHT-GRADIENT GEMMs (dW = dOut^T * In over the 256 staged rows of a block: K = 256, M, N <= 64) are issued by ONE thread
+// as tcgen05.mma with both operands read from shared memory through matrix descriptors and the fp32 accumulators in TMEM
+// (160 columns, alive for the CTA's whole lifetime; k_ngp_bwd2 keeps 20 accumulator registers per thread and spends
+// 1,280 mma.sync + 2,560 ldmatrix per block on them). The activations are staged in the canonical MN-major no-swizzle
+// layout (umma.cuh); the out-gradient of a layer goes to one of two buffers, so the tensor core can still be reading layer
+// L's while the warps stage layer L+1's -- completion is tracked with one mbarrier per buffer. CTA barriers per block: 6
+// (k_ngp_bwd2: 11).  TMEM columns: [0,16) W3r^T  [16,80) W2r  [80,112) W1r  [112,128) W2d^T  [128,160) W1d.
+// -------------------------------------------------------------------------------------------------
+#define B3_WARPS 16
+#define B3_THREADS (B3_WARPS * 32)
+#define B3_ROWS (B3_WARPS * 16)
+#define B3_TMEM_COLS 256
+struct Bwd3Smem {
+    MlpWeightsFwd wf;
+    __align__(128) __half feat[B3_ROWS * 32];
+    __align__(128) __half hid[B3_ROWS * 64];
+    __align__(128) __half rin[B3_ROWS * 32];
+    __align__(128) __half r1[B3_ROWS * 64];
+    __align__(128) __half r2[B3_ROWS * 64];
+    __align__(128) __half dbuf[2][B3_ROWS * 64];  // out-gradient of the layer being processed, alternating
+    __align__(8) uint64_t mbar[2];                // completion of the MMAs that read dbuf[b]
+    uint32_t tmem_base;
+    int blk[2];
+};
+
+// A fragments of this warp's 16 rows <-> canonical tile of C channels (32-bit accesses; a warp touches 128 contiguous bytes)
+template <int KT>
+__device__ __forceinline__ void stage_canon(__half* __restrict__ dst, int C, int row0, const uint32_t (&A)[KT][4], int g, int q) {
+    __half* b0 = dst + (row0 >> 3) * (C * 8) + g * 8 + 2 * q;
+    __half* b1 = b0 + C * 8;
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+        *reinterpret_cast<uint32_t*>(b0 + (2 * kt) * 64) = A[kt][0];
+        *reinterpret_cast<uint32_t*>(b1 + (2 * kt) * 64) = A[kt][1];
+        *reinterpret_cast<uint32_t*>(b0 + (2 * kt + 1) * 64) = A[kt][2];
+        *reinterpret_cast<uint32_t*>(b1 + (2 * kt + 1) * 64) = A[kt][3];
+    }
+}
+template <int KT>
+__device__ __forceinline__ void load_canon(const __half* __restrict__ src, int C, int row0, uint32_t (&A)[1][KT][4], int g, int q) {
+    const __half* b0 = src + (row0 >> 3) * (C * 8) + g * 8 + 2 * q;
+    const __half* b1 = b0 + C * 8;
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+        A[0][kt][0] = *reinterpret_cast<const uint32_t*>(b0 + (2 * kt) * 64);
+        A[0][kt][1] = *reinterpret_cast<const uint32_t*>(b1 + (2 * kt) * 64);
+        A[0][kt][2] = *reinterpret_cast<const uint32_t*>(b0 + (2 * kt + 1) * 64);
+        A[0][kt][3] = *reinterpret_cast<const uint32_t*>(b1 + (2 * kt + 1) * 64);
+    }
+}
+// D[M=64][N] (+)= A^T B over the B3_ROWS staged rows: A = tile of CA channels (its first 64 are M), B = tile of CB channels
+// (its first N are N); one elected thread
+__device__ __forceinline__ void umma_wgrad(uint32_t tmem_d, const __half* A, int CA, const __half* B, int CB, int N, bool first) {
+    const uint32_t idesc = umma_instr_desc_f16(64, N);
+    const uint32_t lbo_a = (uint32_t)CA * 16u, lbo_b = (uint32_t)CB * 16u;  // bytes between 8-row blocks: C/8 * 128
+#pragma unroll 4
+    for (int ks = 0; ks < B3_ROWS / 16; ++ks) {
+        const uint64_t ad = umma_smem_desc(A + (size_t)ks * 2 * CA * 8, lbo_a, 128);
+        const uint64_t bd = umma_smem_desc(B + (size_t)ks * 2 * CB * 8, lbo_b, 128);
+        umma_mma_f16(tmem_d, ad, bd, idesc, (first && ks == 0) ? 0u : 1u);
+    }
+}
+
+__global__ void __launch_bounds__(B3_THREADS, 1)
+k_ngp_bwd3(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_dsigmas, const float* __restrict__ dL_drgbs,
+           const uint4* __restrict__ feat_save, const float* __restrict__ loss_scale, float* __restrict__ grad_enc,
+           float* __restrict__ grad_rgb, uint32_t* __restrict__ dfeat, const int64_t dfeat_stride, int* __restrict__ sched) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Bwd3Smem& S = *reinterpret_cast<Bwd3Smem*>(smem_raw);
+    const __half* wd = reinterpret_cast<const __half*>(net.enc_params_h);
+    const __half* wr = reinterpret_cast<const __half*>(net.rgb_params_h);
+    load_weights_fwd(S.wf, wd, wr, threadIdx.x, B3_THREADS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    const int64_t n = bwd_count(smp);
+    const int32_t* __restrict__ live = smp.live_idx;
+    const int64_t n_mtiles = (n + 15) / 16;
+    const int64_t n_blks = (n_mtiles + B3_WARPS - 1) / B3_WARPS;
+    const float scale = loss_scale ? *loss_scale : 1.0f;
+    const float inv_scale = 1.0f / scale;
+    const int row0 = 16 * warp;
+
+    if (warp == 0) tmem_alloc<B3_TMEM_COLS>(&S.tmem_base);
+    if (threadIdx.x == 0) {
+        mbar_init(&S.mbar[0], 1);
+        mbar_init(&S.mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        S.blk[0] = sched ? atomicAdd(&sched[0], 1) : (int)blockIdx.x;
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = S.tmem_base;
+    uint32_t commits[2] = {0u, 0u};  // MMA batches committed to mbar[b] so far (uniform over the CTA)
+    bool any = false;
+
+    // wait until every MMA batch that read dbuf[b] (and everything issued before it) has completed
+    auto wait_buf = [&](int b) {
+        if (commits[b]) mbar_wait(&S.mbar[b], (commits[b] - 1u) & 1u);
+    };
+    // all rows of the layer are staged: make them visible to the tensor core, then ONE thread issues the layer's GEMM
+    auto issue = [&](int b, uint32_t col, const __half* A, int CA, const __half* B, int CB, int N) {
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tcgen05_fence_after();
+            umma_wgrad(tmem + col, A, CA, B, CB, N, !any);
+            umma_commit(&S.mbar[b]);
+        }
+        commits[b] += 1u;
+    };
+
+    for (int it = 0;; ++it) {
+        const int64_t blk = S.blk[it & 1];
+        if (blk >= n_blks) break;
+        if (threadIdx.x == 0) S.blk[(it + 1) & 1] = sched ? atomicAdd(&sched[0], 1) : (int)(blk + gridDim.x);
+        const int64_t mtile = blk * B3_WARPS + warp;
+        const int64_t base = mtile * 16;
+        bool valid[2];
+        float up_sig[2] = {0.f, 0.f}, up_c0[2] = {0.f, 0.f}, up_c1[2] = {0.f, 0.f};
+        SampleIn sm[2];
+        int64_t src[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t row = base + g + 8 * h;
+            valid[h] = row < n;
+            src[h] = valid[h] ? (live ? (int64_t)__ldg(live + row) : row) : 0;
+            sm[h] = load_sample(smp, src[h], valid[h]);
+            if (valid[h]) {
+                if (q == 0) {
+                    up_sig[h] = __ldg(dL_dsigmas + src[h]);
+                    up_c0[h] = __ldg(dL_drgbs + 3 * src[h]);
+                    up_c1[h] = __ldg(dL_drgbs + 3 * src[h] + 1);
+                } else if (q == 1) {
+                    up_c0[h] = __ldg(dL_drgbs + 3 * src[h] + 2);
+                }
+            }
+        }
+        uint32_t featA[1][2][4];
+        if (live) {
+            const uint32_t* fs = reinterpret_cast<const uint32_t*>(feat_save);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int64_t t2 = (src[h] >> 4) * 2;
+                const int r = (int)(src[h] & 15);
+                const int64_t w0 = (r & 7) * 4 + q;
+                const int sub = r >> 3;
+#pragma unroll
+                for (int kt = 0; kt < 2; ++kt) {
+                    const uint32_t* p = fs + ((t2 + kt) * 32 + w0) * 4 + sub;
+                    featA[0][kt][h] = valid[h] ? __ldg(p) : 0u;
+                    featA[0][kt][2 + h] = valid[h] ? __ldg(p + 2) : 0u;
+                }
+            }
+        } else if (base < n) {
+#pragma unroll
+            for (int kt = 0; kt < 2; ++kt) {
+                const uint4 v = __ldg(feat_save + (mtile * 2 + kt) * 32 + lane);
+                featA[0][kt][0] = v.x; featA[0][kt][1] = v.y; featA[0][kt][2] = v.z; featA[0][kt][3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int kt = 0; kt < 2; ++kt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) featA[0][kt][e] = 0u;
+        }
+        // the previous block's GEMMs still read feat / hid / rin / r1 / r2: the last batch (W1d, buffer 0) completes after
+        // every earlier one (MMAs of one thread complete in order). Also publishes the next ticket.
+        wait_buf(0);
+        __syncthreads();
+
+        // ---- forward recompute, staging each activation as soon as it exists ----
+        stage_canon<2>(S.feat, 32, row0, featA[0], g, q);
+        float h0[2];
+        uint32_t hA[1][1][4];
+        {
+            uint32_t hidA[1][4][4];
+            {
+                float c[1][8][4];
+                mlp_layer<1, 32, 64, LD32>(featA, S.wf.w1d, c, g, q);
+                relu_to_frag<1, 64>(c, hidA);
+            }
+            stage_canon<4>(S.hid, 64, row0, hidA[0], g, q);
+            float c[1][2][4];
+            mlp_layer<1, 64, 16, LD64>(hidA, S.wf.w2d, c, g, q);
+            to_frag<1, 16>(c, hA);
+        }
+        h0[0] = lo_half(hA[0][0][0]);
+        h0[1] = lo_half(hA[0][0][1]);
+        uint32_t doutA[1][1][4];
+        {
+            uint32_t inA[1][2][4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) sh_rows(sm[h], q, inA[0][0][h], inA[0][0][2 + h]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) inA[0][1][e] = hA[0][0][e];
+            stage_canon<2>(S.rin, 32, row0, inA[0], g, q);
+            uint32_t r1A[1][4][4];
+            {
+                float c[1][8][4];
+                mlp_layer<1, 32, 64, LD32>(inA, S.wf.w1r, c, g, q);
+                relu_to_frag<1, 64>(c, r1A);
+            }
+            stage_canon<4>(S.r1, 64, row0, r1A[0], g, q);
+            uint32_t r2A[1][4][4];
+            {
+                float c[1][8][4];
+                mlp_layer<1, 64, 64, LD64>(r1A, S.wf.w2r, c, g, q);
+                relu_to_frag<1, 64>(c, r2A);
+            }
+            stage_canon<4>(S.r2, 64, row0, r2A[0], g, q);
+            float oC[1][1][4];
+            mlp_layer<1, 64, 8, LD64>(r2A, S.wf.w3r, oC, g, q);
+            doutA[0][0][2] = 0u;
+            doutA[0][0][3] = 0u;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float d0 = 0.f, d1 = 0.f;
+                if (valid[h] && q < 2) {
+                    float o0 = oC[0][0][2 * h], o1 = oC[0][0][2 * h + 1];
+                    float s0 = 1.f, s1 = 1.f;
+                    if (net.rgb_act == 1) {
+                        o0 = half_round(1.0f / (1.0f + __expf(-o0)));
+                        o1 = half_round(1.0f / (1.0f + __expf(-o1)));
+                        s0 = o0 * (1.0f - o0);
+                        s1 = o1 * (1.0f - o1);
+                    }
+                    d0 = up_c0[h] * s0 * scale;
+                    d1 = (q == 0) ? up_c1[h] * s1 * scale : 0.f;
+                }
+                doutA[0][0][h] = pack_half2(d0, d1);
+            }
+        }
+
+        // ---- layer rgb-3 : dW3r^T[in 64][out 16] = r2^T dout ; buffer 0 (free: waited above) ----
+        stage_canon<1>(S.dbuf[0], 16, row0, doutA[0], g, q);
+        issue(0, 0u, S.r2, 64, S.dbuf[0], 16, 16);
+        uint32_t dA[1][4][4];  // out-gradient fragments of the 64-wide layers, reused
+        {
+            float c[1][8][4];
+            mlp_layer_dgrad<16, 64, LD64>(doutA, S.wf.w3r, c, lane);
+            uint32_t act[1][4][4];
+            load_canon<4>(S.r2, 64, row0, act, g, q);
+            relu_bwd_to_frag<1, 64>(c, act, dA);
+        }
+        // ---- layer rgb-2 : dW2r[out 64][in 64] = dr2^T r1 ; buffer 1 ----
+        wait_buf(1);
+        stage_canon<4>(S.dbuf[1], 64, row0, dA[0], g, q);
+        issue(1, 16u, S.dbuf[1], 64, S.r1, 64, 64);
+        {
+            float c[1][8][4];
+            mlp_layer_dgrad<64, 64, LD64>(dA, S.wf.w2r, c, lane);
+            uint32_t act[1][4][4];
+            load_canon<4>(S.r1, 64, row0, act, g, q);
+            relu_bwd_to_frag<1, 64>(c, act, dA);
+        }
+        // ---- layer rgb-1 : dW1r[out 64][in 32] = dr1^T rin ; buffer 0 ; only the h half of its input needs a gradient ----
+        wait_buf(0);
+        stage_canon<4>(S.dbuf[0], 64, row0, dA[0], g, q);
+        issue(0, 80u, S.dbuf[0], 64, S.rin, 32, 32);
+        uint32_t dhA[1][1][4];
+        {
+            float c[1][2][4];
+            mlp_layer_dgrad<64, 16, LD32>(dA, S.wf.w1r + 16, c, lane);
+            if (q == 0) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    if (valid[h]) c[0][0][2 * h] += up_sig[h] * expf(fminf(fmaxf(h0[h], -15.f), 15.f)) * scale;
+            }
+            to_frag<1, 16>(c, dhA);
+        }
+        // ---- layer density-2 : dW2d^T[in 64][out 16] = hid^T dh ; buffer 1 ----
+        wait_buf(1);
+        stage_canon<1>(S.dbuf[1], 16, row0, dhA[0], g, q);
+        issue(1, 112u, S.hid, 64, S.dbuf[1], 16, 16);
+        {
+            float c[1][8][4];
+            mlp_layer_dgrad<16, 64, LD64>(dhA, S.wf.w2d, c, lane);
+            uint32_t act[1][4][4];
+            load_canon<4>(S.hid, 64, row0, act, g, q);
+            relu_bwd_to_frag<1, 64>(c, act, dA);
+        }
+        // ---- layer density-1 : dW1d[out 64][in 32] = dhid^T feat ; buffer 0 -> feature gradients ----
+        wait_buf(0);
+        stage_canon<4>(S.dbuf[0], 64, row0, dA[0], g, q);
+        issue(0, 128u, S.dbuf[0], 64, S.feat, 32, 32);
+        any = true;
+        {
+            float c[1][4][4];
+            mlp_layer_dgrad<64, 32, LD32>(dA, S.wf.w1d, c, lane);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int64_t row = base + g + 8 * h;
+                if (!valid[h]) continue;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int level = 4 * j + q;
+                    if (level < net.meta.n_levels)
+                        dfeat[(int64_t)level * dfeat_stride + row] = pack_half2(c[0][j][2 * h], c[0][j][2 * h + 1]);
+                }
+            }
+        }
+    }
+
+    sched_finish(sched);
+    // ---- flush the weight gradients: TMEM -> registers -> fp32 reductions. Row m of an M = 64 accumulator sits in lane
+    //      (m % 16) + 32 (m / 16): warp w < 4 reads its 32 lanes, threads 0..15 of it hold rows 16 w + t ----
+    wait_buf(0);
+    wait_buf(1);
+    tcgen05_fence_after();
+    if (any && warp < 4) {
+        const int m = 16 * warp + lane;  // (meaningful for lane < 16)
+        const uint32_t lane_base = tmem + ((uint32_t)(32 * warp) << 16);
+        uint32_t r[16];
+        auto flush = [&](uint32_t col, int ncols, float* dW, int ld, bool transposed) {
+            for (int c0 = 0; c0 < ncols; c0 += 16) {
+                tmem_ld_32x32b_x16(lane_base + col + (uint32_t)c0, r);
+                if (lane < 16) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float v = __uint_as_float(r[j]) * inv_scale;
+                        float* p = transposed ? dW + (c0 + j) * ld + m : dW + m * ld + c0 + j;
+                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+                    }
+                }
+            }
+        };
+        flush(0u, 16, grad_rgb + 2048 + 4096, 64, true);   // W3r (16 x 64), accumulated transposed
+        flush(16u, 64, grad_rgb + 2048, 64, false);        // W2r (64 x 64)
+        flush(80u, 32, grad_rgb, 32, false);               // W1r (64 x 32)
+        flush(112u, 16, grad_enc + 2048, 64, true);        // W2d (16 x 64), transposed
+        flush(128u, 32, grad_enc, 32, false);              // W1d (64 x 32)
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_free<B3_TMEM_COLS>(tmem);
+}
+
+// -------------------------------------------------------------------------------------------------
 // hash-table gradient scatter: one thread per (sample, level), a warp = 32 CONSECUTIVE samples of one
 // level. Consecutive samples of a ray fall into the same cell at the coarse levels, so equal cells are
 // contiguous lane runs: their 16 corner contributions are summed with a segmented shuffle reduction and
@@ -1093,27 +1434,35 @@ extern "C" int ngp_net_backward_mlp(const NgpNet* net, const NgpSamples* smp, co
         if (dev < 0 || dev >= 64 || !__atomic_load_n(&attr_set[dev], __ATOMIC_ACQUIRE)) {
             NGP_CUDA(cudaFuncSetAttribute(k_ngp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
             NGP_CUDA(cudaFuncSetAttribute(k_ngp_bwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Bwd2Smem)));
+            NGP_CUDA(cudaFuncSetAttribute(k_ngp_bwd3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Bwd3Smem) + 128));
             if (dev >= 0 && dev < 64) __atomic_store_n(&attr_set[dev], 1, __ATOMIC_RELEASE);
         }
     }
-    static int variant = -1;  // NGP_BWD_VARIANT=0 selects the 8-warp all-at-once kernel (also used when re-gathering)
+    static int variant = -1;  // NGP_BWD_VARIANT (env, read once): 2 = tcgen05 weight gradients (default), 1 = k_ngp_bwd2, 0 = k_ngp_bwd
     if (variant < 0) {
         const char* e = getenv("NGP_BWD_VARIANT");
-        variant = e ? atoi(e) : 1;
+        variant = e ? atoi(e) : 2;
     }
     const int64_t n_mtiles = (smp->n + 15) / 16;
-    if (smp->live_idx && (!smp->n_live_dev || variant == 0 || !feat_save)) return NGP_EINVAL;  // live list: k_ngp_bwd2 only
+    if (smp->live_idx && (!smp->n_live_dev || variant == 0 || !feat_save)) return NGP_EINVAL;  // live list: k_ngp_bwd2/3 only
     if (variant == 0 || !feat_save) {
         const int64_t n_blks = (n_mtiles + BWD_WARPS - 1) / BWD_WARPS;
         const int grid = (int)(n_blks < (int64_t)ngp_sm_count() ? n_blks : ngp_sm_count());
         k_ngp_bwd<<<grid, BWD_THREADS, sizeof(BwdSmem), (cudaStream_t)stream>>>(
             *net, *smp, dL_dsigmas, dL_drgbs, (const uint4*)feat_save, loss_scale, grad_enc, grad_rgb, (uint32_t*)workspace,
             n_mtiles * 16);
-    } else {
+    } else if (variant == 1) {
         const int64_t n_blks = (n_mtiles + B2_WARPS - 1) / B2_WARPS;
         const int grid = (int)(n_blks < (int64_t)ngp_sm_count() ? n_blks : ngp_sm_count());
         int* sched = sched_slot((cudaStream_t)stream);
         k_ngp_bwd2<<<grid, B2_THREADS, sizeof(Bwd2Smem), (cudaStream_t)stream>>>(
+            *net, *smp, dL_dsigmas, dL_drgbs, (const uint4*)feat_save, loss_scale, grad_enc, grad_rgb, (uint32_t*)workspace,
+            n_mtiles * 16, sched);
+    } else {
+        const int64_t n_blks = (n_mtiles + B3_WARPS - 1) / B3_WARPS;
+        const int grid = (int)(n_blks < (int64_t)ngp_sm_count() ? n_blks : ngp_sm_count());
+        int* sched = sched_slot((cudaStream_t)stream);
+        k_ngp_bwd3<<<grid, B3_THREADS, sizeof(Bwd3Smem) + 128, (cudaStream_t)stream>>>(
             *net, *smp, dL_dsigmas, dL_drgbs, (const uint4*)feat_save, loss_scale, grad_enc, grad_rgb, (uint32_t*)workspace,
             n_mtiles * 16, sched);
     }

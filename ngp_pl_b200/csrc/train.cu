@@ -287,7 +287,8 @@ __global__ void k_train_grad_scale(float* __restrict__ scalars, int* __restrict_
 // compositing forward + NeRFLoss + compositing backward of one ray in ONE pass by one warp (the loss gradient of a ray
 // depends on that ray's composited colour / opacity only): k_train_composite_fw + k_nerf_loss_grad + k_train_composite_bw
 // without the two extra launches and with the second sweep over the ray's samples hitting L1/L2.
-__global__ void k_train_composite_loss(const NgpTrainCfg cfg, const int* __restrict__ n_samples, const int* __restrict__ offsets,
+#define CL_WARPS 8  // rays per block of k_train_composite_loss
+__global__ void __launch_bounds__(CL_WARPS * 32) k_train_composite_loss(const NgpTrainCfg cfg, const int* __restrict__ n_samples, const int* __restrict__ offsets,
                                        const float* __restrict__ sigmas, const float* __restrict__ rgbs,
                                        const float* __restrict__ deltas, const float* __restrict__ ts,
                                        const float* __restrict__ rgb_gt, float* __restrict__ rgb, float* __restrict__ opacity,
@@ -295,11 +296,14 @@ __global__ void k_train_composite_loss(const NgpTrainCfg cfg, const int* __restr
                                        float* __restrict__ scalars, int* __restrict__ live_idx, int* __restrict__ counters,
                                        const float* __restrict__ bg_dev) {
     const float bg[3] = {bg_dev ? bg_dev[0] : cfg.bg[0], bg_dev ? bg_dev[1] : cfg.bg[1], bg_dev ? bg_dev[2] : cfg.bg[2]};
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (w >= cfg.n_rays) return;
+    // (n_rays is a multiple of the rays per block or the last block's spare warps idle on ray n_rays - 1 with n = 0 and
+    // contribute nothing: every warp must reach the block barriers below)
+    const int w_raw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const bool real = w_raw < cfg.n_rays;
+    const int w = real ? w_raw : cfg.n_rays - 1;
     const int64_t start = offsets[w];
-    int n = n_samples[w];
+    int n = real ? n_samples[w] : 0;
     if (start + n > cfg.max_total_samples) n = (int)max((int64_t)0, cfg.max_total_samples - start);
     const float* sg = sigmas + start;
     const float* dl = deltas + start;
@@ -318,39 +322,75 @@ __global__ void k_train_composite_loss(const NgpTrainCfg cfg, const int* __restr
     const float3 dC = make_float3(2.0f * ex * inv_n * (1.0f / 3.0f), 2.0f * ey * inv_n * (1.0f / 3.0f), 2.0f * ez * inv_n * (1.0f / 3.0f));
     const float op = o.opacity + 1e-10f;
     const float lg = logf(op);
-    if (lane == 0) {
+    if (lane == 0 && real) {
         opacity[w] = o.opacity;
         depth[w] = o.depth;
         rgb[3 * w] = out.x; rgb[3 * w + 1] = out.y; rgb[3 * w + 2] = out.z;
-        if (o.total_samples) atomicAdd(&counters[1], o.total_samples);
-        atomicAdd(&scalars[4], ex * ex + ey * ey + ez * ez);
-        atomicAdd(&scalars[5], -op * lg);
     }
-    if (n == 0) return;
     // backward: the background term routes the colour gradient into the opacity gradient
-    const float dO = cfg.lambda_opacity * (-lg - 1.0f) * inv_n - (dC.x * bg[0] + dC.y * bg[1] + dC.z * bg[2]);
-    float* ds = dsigmas + start;
-    float* dc = drgbs + 3 * start;
     float m = 0.f;
-    const int n_comp = composite_ray_warp_bwd(
-        n, cfg.T_threshold, lane, dO, 0.f, dC, o.opacity, o.depth, make_float3(o.r, o.g, o.b),
-        [&](int i) { return __ldg(sg + i); }, [&](int i) { return __ldg(dl + i); }, [&](int i) { return __ldg(tt + i); },
-        [&](int i) { return make_float3(__ldg(cl + 3 * i), __ldg(cl + 3 * i + 1), __ldg(cl + 3 * i + 2)); },
-        [&](int) { return 0.f; }, [&](int) { return 0.f; },
-        [&](int i, float v) {
-            ds[i] = v;
-            m = fmaxf(m, fabsf(v * fminf(__ldg(sg + i), 3.2690173e6f)));
-        },
-        [&](int i, float3 v) {
-            dc[3 * i] = v.x; dc[3 * i + 1] = v.y; dc[3 * i + 2] = v.z;
-            m = fmaxf(m, fmaxf(fabsf(v.x), fmaxf(fabsf(v.y), fabsf(v.z))));
-        });
-    m = warp_max(m);
-    if (lane == 0 && m > 0.f && m < INFINITY) atomicMax(reinterpret_cast<int*>(scalars), __float_as_int(m));
-    if (live_idx) {
-        int at = 0;
-        if (lane == 0) at = atomicAdd(&counters[4], n_comp);
-        at = __shfl_sync(0xffffffffu, at, 0);
+    int n_comp = 0;
+    if (n > 0) {
+        const float dO = cfg.lambda_opacity * (-lg - 1.0f) * inv_n - (dC.x * bg[0] + dC.y * bg[1] + dC.z * bg[2]);
+        float* ds = dsigmas + start;
+        float* dc = drgbs + 3 * start;
+        n_comp = composite_ray_warp_bwd(
+            n, cfg.T_threshold, lane, dO, 0.f, dC, o.opacity, o.depth, make_float3(o.r, o.g, o.b),
+            [&](int i) { return __ldg(sg + i); }, [&](int i) { return __ldg(dl + i); }, [&](int i) { return __ldg(tt + i); },
+            [&](int i) { return make_float3(__ldg(cl + 3 * i), __ldg(cl + 3 * i + 1), __ldg(cl + 3 * i + 2)); },
+            [&](int) { return 0.f; }, [&](int) { return 0.f; },
+            [&](int i, float v) {
+                ds[i] = v;
+                m = fmaxf(m, fabsf(v * fminf(__ldg(sg + i), 3.2690173e6f)));
+            },
+            [&](int i, float3 v) {
+                dc[3 * i] = v.x; dc[3 * i + 1] = v.y; dc[3 * i + 2] = v.z;
+                m = fmaxf(m, fmaxf(fabsf(v.x), fmaxf(fabsf(v.y), fabsf(v.z))));
+            });
+        m = warp_max(m);
+    }
+    // Per-ray sums, the loss-scale maximum and the live-list allocation go through ONE set of atomics per BLOCK (8 rays):
+    // five same-address atomics per ray serialise in the L2 atomic unit -- 41 k of them made this kernel 41 us
+    // (profiles/r02_launches_step_c2.md) although its arithmetic is a few microseconds.
+    __shared__ float s_se[CL_WARPS], s_ent[CL_WARPS], s_m[CL_WARPS];
+    __shared__ int s_tot[CL_WARPS], s_comp[CL_WARPS], s_base;
+    const int wib = threadIdx.x >> 5;
+    if (lane == 0) {
+        s_se[wib] = ex * ex + ey * ey + ez * ez;
+        s_ent[wib] = -op * lg;
+        s_m[wib] = (m > 0.f && m < INFINITY) ? m : 0.f;
+        s_tot[wib] = o.total_samples;
+        s_comp[wib] = n_comp;
+    }
+    __syncthreads();
+    if (wib == 0) {
+        const bool has = lane < CL_WARPS && (blockIdx.x * CL_WARPS + lane) < cfg.n_rays;
+        float se = has ? s_se[lane] : 0.f, ent = has ? s_ent[lane] : 0.f, mm = has ? s_m[lane] : 0.f;
+        int tot = has ? s_tot[lane] : 0, comp = has ? s_comp[lane] : 0;
+        int pre = comp;  // inclusive prefix of the rays' composited counts
+#pragma unroll
+        for (int o2 = 1; o2 < CL_WARPS; o2 <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, pre, o2);
+            if (lane >= o2) pre += u;
+        }
+        if (has) s_comp[lane] = pre - comp;  // exclusive offset of ray `lane` inside the block's range
+        se = warp_sum(se);
+        ent = warp_sum(ent);
+        mm = warp_max(mm);
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o2);
+        const int block_comp = __shfl_sync(0xffffffffu, pre, CL_WARPS - 1);
+        if (lane == 0) {
+            if (tot) atomicAdd(&counters[1], tot);
+            atomicAdd(&scalars[4], se);
+            atomicAdd(&scalars[5], ent);
+            if (mm > 0.f) atomicMax(reinterpret_cast<int*>(scalars), __float_as_int(mm));
+            s_base = (live_idx && block_comp) ? atomicAdd(&counters[4], block_comp) : 0;
+        }
+    }
+    __syncthreads();
+    if (live_idx && n_comp > 0) {
+        const int at = s_base + s_comp[wib];
         for (int i = lane; i < n_comp; i += 32) live_idx[at + i] = (int)(start + i);
     }
 }
@@ -367,7 +407,7 @@ extern "C" int ngp_render_train_step(const NgpNet* net, const NgpTrainCfg* cfg, 
     NgpSamples smp = train_samples(cfg, b);
     rc = ngp_net_forward(net, &smp, 1, b->sigmas, b->rgbs, nullptr, b->feat_save, stream);
     if (rc) return rc;
-    k_train_composite_loss<<<ngp_div_up((int64_t)n * 32, 128), 128, 0, st>>>(
+    k_train_composite_loss<<<ngp_div_up(n, CL_WARPS), CL_WARPS * 32, 0, st>>>(
         *cfg, b->n_samples, b->offsets, b->sigmas, b->rgbs, b->deltas, b->ts, rgb_gt, b->rgb, b->opacity, b->depth, b->dsigmas,
         b->drgbs, b->scalars, b->live_idx, b->counters, b->bg_dev);
     NGP_CHECK_LAUNCH();

@@ -303,6 +303,8 @@ class NGP(nn.Module):
         if self.rgb_act == 'None' and not kwargs.get('output_radiance', False):
             raise NotImplementedError("HDR tonemapper path (use_exposure) is outside the hot path")
         need_cuda(x, "NGP.forward")
+        self.xyz_encoder._half.training_forward(self.xyz_encoder.params)  # tinycudann re-casts its weights every forward
+        self.rgb_net._half.training_forward(self.rgb_net.params)
         sig, rgb = _NGPForward.apply(x, d, self.xyz_encoder.params, self.rgb_net.params, self)
         if self.rgb_act == 'None':
             from .custom_functions import TruncExp

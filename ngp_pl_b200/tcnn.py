@@ -29,10 +29,10 @@ def _st():
 
 class _HalfCopy:
     """fp16 working copy of an fp32 parameter vector. tinycudann re-casts its parameters on every forward; so does this
-    whenever the parameter can have changed behind autograd's back: always while it requires grad and grad mode is on (an
-    optimiser that writes through `p.data` -- apex FusedAdam, the reference's choice at train.py:128-134 -- or an EMA swap
-    does NOT bump `p._version`), otherwise (inference) only when (pointer, version) changed. ~25 us for the 11.5 M
-    parameters. `invalidate()` forces the next call to re-cast."""
+    whenever the parameter can have changed behind autograd's back: the modules call `training_forward()` at the top of
+    every forward that runs with grad mode on and a parameter that requires grad (an optimiser that writes through `p.data`
+    -- apex FusedAdam, the reference's choice at train.py:128-134 -- or an EMA swap does NOT bump `p._version`); otherwise
+    (inference) the copy is refreshed only when (pointer, version) changed. ~25 us for the 11.5 M parameters."""
 
     def __init__(self):
         self.buf = None
@@ -41,12 +41,17 @@ class _HalfCopy:
     def invalidate(self):
         self.key = None
 
+    def training_forward(self, p):
+        """called OUTSIDE the autograd.Function (grad mode is off inside Function.forward): re-cast if this is a training forward"""
+        if p.requires_grad and torch.is_grad_enabled():
+            self.key = None
+
     def get(self, p):
         key = (p.data_ptr(), p._version, p.device)
         if self.buf is None or self.buf.device != p.device or self.buf.numel() != p.numel():
             self.buf = torch.empty(p.numel(), device=p.device, dtype=torch.float16)
             self.key = None
-        if key != self.key or (p.requires_grad and torch.is_grad_enabled()):
+        if key != self.key:
             with torch.cuda.device(p.device):
                 _lib.check(_lib.lib().ngp_cast_params(p.data_ptr(), self.buf.data_ptr(), p.numel(), _st()), "cast_params")
             self.key = key
@@ -61,6 +66,9 @@ class _FixedHalf:
         self.buf = buf
 
     def invalidate(self):
+        pass
+
+    def training_forward(self, p):
         pass
 
     def get(self, p):
@@ -127,6 +135,7 @@ class NetworkWithInputEncoding(nn.Module):
         """x in [0,1]^3 (N,3) -> fp16 (N,16). Differentiable w.r.t. params."""
         from .models.networks import _DensityFeatures, need_cuda
         need_cuda(x, "tcnn.NetworkWithInputEncoding")
+        self._half.training_forward(self.params)
         return _DensityFeatures.apply(x, self.params, self)
 
 
@@ -159,4 +168,5 @@ class Network(nn.Module):
     def forward(self, x):
         from .models.networks import _RgbMlp, need_cuda
         need_cuda(x, "tcnn.Network")
+        self._half.training_forward(self.params)
         return _RgbMlp.apply(x, self.params, self)
