@@ -979,17 +979,22 @@ k_ngp_bwd2(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_
 }
 
 // -------------------------------------------------------------------------------------------------
-// backward, tcgen05 variant (default): the dgrad chain stays on mma.sync fragments in the sixteen warps, but the five
-// WEIGHT-GRADIENT GEMMs (dW = dOut^T * In over the 256 staged rows of a block: K = 256, M, N <= 64) are issued by ONE thread
-// as tcgen05.mma with both operands read from shared memory through matrix descriptors and the fp32 accumulators in TMEM
-// (160 columns, alive for the CTA's whole lifetime; k_ngp_bwd2 keeps 20 accumulator registers per thread and spends
-// 1,280 mma.sync + 2,560 ldmatrix per block on them). The activations are staged in the canonical MN-major no-swizzle
-// layout (umma.cuh); the out-gradient of a layer goes to one of two buffers, so the tensor core can still be reading layer
-// L's while the warps stage layer L+1's -- completion is tracked with one mbarrier per buffer. CTA barriers per block: 6
-// (k_ngp_bwd2: 11).  TMEM columns: [0,16) W3r^T  [16,80) W2r  [80,112) W1r  [112,128) W2d^T  [128,160) W1d.
+// backward, tcgen05 variant (default): the dgrad chain stays on mma.sync fragments in sixteen ROW warps, but the five
+// WEIGHT-GRADIENT GEMMs (dW = dOut^T * In over the 256 staged rows of a block: K = 256, M, N <= 64) are issued by a
+// seventeenth ISSUER warp as tcgen05.mma with both operands read from shared memory through matrix descriptors and the fp32
+// accumulators in TMEM (160 columns, alive for the CTA's whole lifetime; k_ngp_bwd2 keeps 20 accumulator registers per
+// thread and spends 1,280 mma.sync + 2,560 ldmatrix per block on them). The activations are staged in the canonical
+// MN-major no-swizzle layout (umma.cuh); the out-gradient of a layer goes to one of two buffers, so the tensor core can
+// still be reading layer L's while the warps stage layer L+1's.
+// Synchronisation is by mbarriers, not CTA barriers: a row thread that has staged its rows of a layer ARRIVES on that
+// layer's `staged` barrier and carries on with its dgrad; the issuer WAITS on it, issues the 16 MMAs of the layer's GEMM and
+// commits them to the `done` barrier of the buffer they read, which row threads wait on only before they overwrite that
+// buffer two layers later. One CTA barrier per 256-row block is left (ticket broadcast + reuse of the activation tiles);
+// k_ngp_bwd2 has eleven. TMEM columns: [0,16) W3r^T  [16,80) W2r  [80,112) W1r  [112,128) W2d^T  [128,160) W1d.
 // -------------------------------------------------------------------------------------------------
 #define B3_WARPS 16
-#define B3_THREADS (B3_WARPS * 32)
+#define B3_ROW_THREADS (B3_WARPS * 32)
+#define B3_THREADS (B3_ROW_THREADS + 32)
 #define B3_ROWS (B3_WARPS * 16)
 #define B3_TMEM_COLS 256
 struct Bwd3Smem {
@@ -1000,7 +1005,8 @@ struct Bwd3Smem {
     __align__(128) __half r1[B3_ROWS * 64];
     __align__(128) __half r2[B3_ROWS * 64];
     __align__(128) __half dbuf[2][B3_ROWS * 64];  // out-gradient of the layer being processed, alternating
-    __align__(8) uint64_t mbar[2];                // completion of the MMAs that read dbuf[b]
+    __align__(8) uint64_t done[2];                // completion of the MMAs that read dbuf[b]
+    uint64_t staged[5];                           // all rows of layer L are staged (B3_ROW_THREADS arrivals per block)
     uint32_t tmem_base;
     int blk[2];
 };
@@ -1035,12 +1041,17 @@ __device__ __forceinline__ void load_canon(const __half* __restrict__ src, int C
 __device__ __forceinline__ void umma_wgrad(uint32_t tmem_d, const __half* A, int CA, const __half* B, int CB, int N, bool first) {
     const uint32_t idesc = umma_instr_desc_f16(64, N);
     const uint32_t lbo_a = (uint32_t)CA * 16u, lbo_b = (uint32_t)CB * 16u;  // bytes between 8-row blocks: C/8 * 128
+    uint64_t ad = umma_smem_desc(A, lbo_a, 128), bd = umma_smem_desc(B, lbo_b, 128);
+    const uint64_t a_step = (uint64_t)((2u * lbo_a) >> 4), b_step = (uint64_t)((2u * lbo_b) >> 4);  // 16 rows, in 16-byte units
 #pragma unroll 4
     for (int ks = 0; ks < B3_ROWS / 16; ++ks) {
-        const uint64_t ad = umma_smem_desc(A + (size_t)ks * 2 * CA * 8, lbo_a, 128);
-        const uint64_t bd = umma_smem_desc(B + (size_t)ks * 2 * CB * 8, lbo_b, 128);
         umma_mma_f16(tmem_d, ad, bd, idesc, (first && ks == 0) ? 0u : 1u);
+        ad += a_step;  // the start-address field is the low 14 bits; the tiles end below 256 KB, so no carry leaves it
+        bd += b_step;
     }
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(mbar)) : "memory");
 }
 
 __global__ void __launch_bounds__(B3_THREADS, 1)
@@ -1054,6 +1065,7 @@ k_ngp_bwd3(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_
     load_weights_fwd(S.wf, wd, wr, threadIdx.x, B3_THREADS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    const bool issuer = warp == B3_WARPS;
     const int64_t n = bwd_count(smp);
     const int32_t* __restrict__ live = smp.live_idx;
     const int64_t n_mtiles = (n + 15) / 16;
@@ -1064,8 +1076,10 @@ k_ngp_bwd3(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_
 
     if (warp == 0) tmem_alloc<B3_TMEM_COLS>(&S.tmem_base);
     if (threadIdx.x == 0) {
-        mbar_init(&S.mbar[0], 1);
-        mbar_init(&S.mbar[1], 1);
+        mbar_init(&S.done[0], 1);
+        mbar_init(&S.done[1], 1);
+#pragma unroll
+        for (int l = 0; l < 5; ++l) mbar_init(&S.staged[l], B3_ROW_THREADS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         S.blk[0] = sched ? atomicAdd(&sched[0], 1) : (int)blockIdx.x;
     }
@@ -1073,29 +1087,44 @@ k_ngp_bwd3(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem = S.tmem_base;
-    uint32_t commits[2] = {0u, 0u};  // MMA batches committed to mbar[b] so far (uniform over the CTA)
-    bool any = false;
+    uint32_t commits[2] = {0u, 0u};  // MMA batches committed to done[b] so far (every thread counts the same)
+    int n_done = 0;                  // blocks processed by this CTA
 
-    // wait until every MMA batch that read dbuf[b] (and everything issued before it) has completed
+    // wait until the most recent MMA batch that read dbuf[b] (and everything issued before it) has completed
     auto wait_buf = [&](int b) {
-        if (commits[b]) mbar_wait(&S.mbar[b], (commits[b] - 1u) & 1u);
-    };
-    // all rows of the layer are staged: make them visible to the tensor core, then ONE thread issues the layer's GEMM
-    auto issue = [&](int b, uint32_t col, const __half* A, int CA, const __half* B, int CB, int N) {
-        fence_proxy_async_smem();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            tcgen05_fence_after();
-            umma_wgrad(tmem + col, A, CA, B, CB, N, !any);
-            umma_commit(&S.mbar[b]);
-        }
-        commits[b] += 1u;
+        if (commits[b]) mbar_wait(&S.done[b], (commits[b] - 1u) & 1u);
     };
 
     for (int it = 0;; ++it) {
         const int64_t blk = S.blk[it & 1];
         if (blk >= n_blks) break;
         if (threadIdx.x == 0) S.blk[(it + 1) & 1] = sched ? atomicAdd(&sched[0], 1) : (int)(blk + gridDim.x);
+        ++n_done;
+
+        if (issuer) {
+            // ================= issuer warp: one GEMM per layer, as soon as the layer's rows are staged =================
+            __syncthreads();  // (the block's CTA barrier: see the row warps)
+            const uint32_t par = (uint32_t)it & 1u;
+            const bool first = it == 0;
+            if (lane == 0) {
+                mbar_wait(&S.staged[0], par); tcgen05_fence_after();
+                umma_wgrad(tmem + 0u, S.r2, 64, S.dbuf[0], 16, 16, first);   umma_commit(&S.done[0]);
+                mbar_wait(&S.staged[1], par); tcgen05_fence_after();
+                umma_wgrad(tmem + 16u, S.dbuf[1], 64, S.r1, 64, 64, first);  umma_commit(&S.done[1]);
+                mbar_wait(&S.staged[2], par); tcgen05_fence_after();
+                umma_wgrad(tmem + 80u, S.dbuf[0], 64, S.rin, 32, 32, first); umma_commit(&S.done[0]);
+                mbar_wait(&S.staged[3], par); tcgen05_fence_after();
+                umma_wgrad(tmem + 112u, S.hid, 64, S.dbuf[1], 16, 16, first); umma_commit(&S.done[1]);
+                mbar_wait(&S.staged[4], par); tcgen05_fence_after();
+                umma_wgrad(tmem + 128u, S.dbuf[0], 64, S.feat, 32, 32, first); umma_commit(&S.done[0]);
+            }
+            __syncwarp();
+            commits[0] += 3u;
+            commits[1] += 2u;
+            continue;
+        }
+
+        // ================= row warps =================
         const int64_t mtile = blk * B3_WARPS + warp;
         const int64_t base = mtile * 16;
         bool valid[2];
@@ -1146,8 +1175,9 @@ k_ngp_bwd3(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_
 #pragma unroll
                 for (int e = 0; e < 4; ++e) featA[0][kt][e] = 0u;
         }
-        // the previous block's GEMMs still read feat / hid / rin / r1 / r2: the last batch (W1d, buffer 0) completes after
-        // every earlier one (MMAs of one thread complete in order). Also publishes the next ticket.
+        // the previous block's GEMMs still read feat / hid / rin / r1 / r2: its last batch (W1d, buffer 0) completes after
+        // every earlier one (the MMAs of one thread complete in order). The CTA barrier also publishes the next ticket and
+        // keeps a fast thread from arriving on a `staged` barrier whose previous phase is still open.
         wait_buf(0);
         __syncthreads();
 
@@ -1216,7 +1246,9 @@ k_ngp_bwd3(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_
 
         // ---- layer rgb-3 : dW3r^T[in 64][out 16] = r2^T dout ; buffer 0 (free: waited above) ----
         stage_canon<1>(S.dbuf[0], 16, row0, doutA[0], g, q);
-        issue(0, 0u, S.r2, 64, S.dbuf[0], 16, 16);
+        fence_proxy_async_smem();
+        mbar_arrive(&S.staged[0]);
+        commits[0] += 1u;
         uint32_t dA[1][4][4];  // out-gradient fragments of the 64-wide layers, reused
         {
             float c[1][8][4];
@@ -1228,7 +1260,9 @@ k_ngp_bwd3(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_
         // ---- layer rgb-2 : dW2r[out 64][in 64] = dr2^T r1 ; buffer 1 ----
         wait_buf(1);
         stage_canon<4>(S.dbuf[1], 64, row0, dA[0], g, q);
-        issue(1, 16u, S.dbuf[1], 64, S.r1, 64, 64);
+        fence_proxy_async_smem();
+        mbar_arrive(&S.staged[1]);
+        commits[1] += 1u;
         {
             float c[1][8][4];
             mlp_layer_dgrad<64, 64, LD64>(dA, S.wf.w2r, c, lane);
@@ -1239,7 +1273,9 @@ k_ngp_bwd3(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_
         // ---- layer rgb-1 : dW1r[out 64][in 32] = dr1^T rin ; buffer 0 ; only the h half of its input needs a gradient ----
         wait_buf(0);
         stage_canon<4>(S.dbuf[0], 64, row0, dA[0], g, q);
-        issue(0, 80u, S.dbuf[0], 64, S.rin, 32, 32);
+        fence_proxy_async_smem();
+        mbar_arrive(&S.staged[2]);
+        commits[0] += 1u;
         uint32_t dhA[1][1][4];
         {
             float c[1][2][4];
@@ -1254,7 +1290,9 @@ k_ngp_bwd3(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_
         // ---- layer density-2 : dW2d^T[in 64][out 16] = hid^T dh ; buffer 1 ----
         wait_buf(1);
         stage_canon<1>(S.dbuf[1], 16, row0, dhA[0], g, q);
-        issue(1, 112u, S.hid, 64, S.dbuf[1], 16, 16);
+        fence_proxy_async_smem();
+        mbar_arrive(&S.staged[3]);
+        commits[1] += 1u;
         {
             float c[1][8][4];
             mlp_layer_dgrad<16, 64, LD64>(dhA, S.wf.w2d, c, lane);
@@ -1265,8 +1303,9 @@ k_ngp_bwd3(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_
         // ---- layer density-1 : dW1d[out 64][in 32] = dhid^T feat ; buffer 0 -> feature gradients ----
         wait_buf(0);
         stage_canon<4>(S.dbuf[0], 64, row0, dA[0], g, q);
-        issue(0, 128u, S.dbuf[0], 64, S.feat, 32, 32);
-        any = true;
+        fence_proxy_async_smem();
+        mbar_arrive(&S.staged[4]);
+        commits[0] += 1u;
         {
             float c[1][4][4];
             mlp_layer_dgrad<64, 32, LD32>(dA, S.wf.w1d, c, lane);
@@ -1290,7 +1329,7 @@ k_ngp_bwd3(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_
     wait_buf(0);
     wait_buf(1);
     tcgen05_fence_after();
-    if (any && warp < 4) {
+    if (n_done > 0 && warp < 4) {
         const int m = 16 * warp + lane;  // (meaningful for lane < 16)
         const uint32_t lane_base = tmem + ((uint32_t)(32 * warp) << 16);
         uint32_t r[16];
