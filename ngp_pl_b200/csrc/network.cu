@@ -1006,7 +1006,7 @@ struct Bwd3Smem {
     __align__(128) __half r2[B3_ROWS * 64];
     __align__(128) __half dbuf[2][B3_ROWS * 64];  // out-gradient of the layer being processed, alternating
     __align__(8) uint64_t done[2];                // completion of the MMAs that read dbuf[b]
-    uint64_t staged[5];                           // all rows of layer L are staged (B3_ROW_THREADS arrivals per block)
+    uint64_t staged[5];                           // all rows of layer L are staged (one arrival per row warp and block)
     uint32_t tmem_base;
     int blk[2];
 };
@@ -1079,7 +1079,7 @@ k_ngp_bwd3(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_
         mbar_init(&S.done[0], 1);
         mbar_init(&S.done[1], 1);
 #pragma unroll
-        for (int l = 0; l < 5; ++l) mbar_init(&S.staged[l], B3_ROW_THREADS);
+        for (int l = 0; l < 5; ++l) mbar_init(&S.staged[l], B3_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         S.blk[0] = sched ? atomicAdd(&sched[0], 1) : (int)blockIdx.x;
     }
@@ -1247,7 +1247,8 @@ k_ngp_bwd3(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_
         // ---- layer rgb-3 : dW3r^T[in 64][out 16] = r2^T dout ; buffer 0 (free: waited above) ----
         stage_canon<1>(S.dbuf[0], 16, row0, doutA[0], g, q);
         fence_proxy_async_smem();
-        mbar_arrive(&S.staged[0]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.staged[0]);
         commits[0] += 1u;
         uint32_t dA[1][4][4];  // out-gradient fragments of the 64-wide layers, reused
         {
@@ -1261,7 +1262,8 @@ k_ngp_bwd3(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_
         wait_buf(1);
         stage_canon<4>(S.dbuf[1], 64, row0, dA[0], g, q);
         fence_proxy_async_smem();
-        mbar_arrive(&S.staged[1]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.staged[1]);
         commits[1] += 1u;
         {
             float c[1][8][4];
@@ -1274,7 +1276,8 @@ k_ngp_bwd3(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_
         wait_buf(0);
         stage_canon<4>(S.dbuf[0], 64, row0, dA[0], g, q);
         fence_proxy_async_smem();
-        mbar_arrive(&S.staged[2]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.staged[2]);
         commits[0] += 1u;
         uint32_t dhA[1][1][4];
         {
@@ -1291,7 +1294,8 @@ k_ngp_bwd3(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_
         wait_buf(1);
         stage_canon<1>(S.dbuf[1], 16, row0, dhA[0], g, q);
         fence_proxy_async_smem();
-        mbar_arrive(&S.staged[3]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.staged[3]);
         commits[1] += 1u;
         {
             float c[1][8][4];
@@ -1304,7 +1308,8 @@ k_ngp_bwd3(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_
         wait_buf(0);
         stage_canon<4>(S.dbuf[0], 64, row0, dA[0], g, q);
         fence_proxy_async_smem();
-        mbar_arrive(&S.staged[4]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.staged[4]);
         commits[0] += 1u;
         {
             float c[1][4][4];
@@ -1337,11 +1342,17 @@ k_ngp_bwd3(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_
             for (int c0 = 0; c0 < ncols; c0 += 16) {
                 tmem_ld_32x32b_x16(lane_base + col + (uint32_t)c0, r);
                 if (lane < 16) {
+                    if (transposed) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float v = __uint_as_float(r[j]) * inv_scale;
-                        float* p = transposed ? dW + (c0 + j) * ld + m : dW + m * ld + c0 + j;
-                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+                        for (int j = 0; j < 16; ++j)
+                            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dW + (c0 + j) * ld + m),
+                                         "f"(__uint_as_float(r[j]) * inv_scale)
+                                         : "memory");
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4)  // 16 consecutive columns of one row: four 16-byte reductions
+                            red_add_f32x4(dW + m * ld + c0 + j, __uint_as_float(r[j]) * inv_scale, __uint_as_float(r[j + 1]) * inv_scale,
+                                          __uint_as_float(r[j + 2]) * inv_scale, __uint_as_float(r[j + 3]) * inv_scale);
                     }
                 }
             }
