@@ -531,8 +531,8 @@ def run_b200(args):
         ks = [entry("k_ngp_fwd", "hbm", t["fwd"], n_samples, 512.0, hbm, "GB/s", "512 B/sample table gathers, every marched sample"),
               entry("k_grid_scatter_merged", "hbm", t["sc"], n_bwd, 1024.0, hbm, "GB/s",
                     "1,024 B/sample gradient RMW, composited samples only"),
-              entry("k_ngp_bwd2", "tensor", t["mlp"], n_bwd, 40960.0, tf, "TFLOP/s",
-                    "40,960 FLOP/sample dgrad+wgrad, composited samples only")]
+              entry("k_ngp_bwd3", "tensor", t["mlp"], n_bwd, 40960.0, tf, "TFLOP/s",
+                    "40,960 FLOP/sample dgrad (mma.sync) + wgrad (tcgen05.mma, TMEM accumulators), composited samples only")]
         roof = dict(max(ks, key=lambda e: e["ms_per_launch"]))  # the dominant kernel of the step
         roof["peak_source"] = which
         roof["traffic_source"] = traffic_src
@@ -541,7 +541,7 @@ def run_b200(args):
                          "(in-step state), ms_per_launch_cold_l2 = after a 256 MB flush"
         roof["note"] = ("hash table (22.9 MB fp16) and its fp32 gradient (45.8 MB) are L2-resident on B200, so DRAM traffic stays far "
                         "below the algorithmic bytes; the physical limiters are L1 wavefronts of divergent 4-B gathers / 8-B reductions "
-                        "and, for the MLP backward, shared-memory latency (profiles/)")
+                        "and, for the MLP backward, the latency of its per-row dgrad chain (profiles/)")
 
     # ---- 800x800 render FPS with the trained model (BASELINE config 3), views sharded over the ranks ------------
     fps = None

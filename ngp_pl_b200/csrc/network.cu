@@ -1090,6 +1090,61 @@ k_ngp_bwd3(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_
     uint32_t commits[2] = {0u, 0u};  // MMA batches committed to done[b] so far (every thread counts the same)
     int n_done = 0;                  // blocks processed by this CTA
 
+    // ---- software-pipelined row fetch (row warps): state of the NEXT block's two rows of this lane ----
+    bool pre_valid[2] = {false, false};
+    int64_t pre_src[2] = {0, 0};
+    int pre_ridx[2] = {-1, -1};
+    float pre_t[2] = {0.f, 0.f};
+    float pre_up[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+    uint32_t pre_feat[2][4] = {{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}};
+    auto fetch_hop1 = [&](int64_t nblk) {  // which sample does each of my rows stand for
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t row = (nblk * B3_WARPS + warp) * 16 + g + 8 * h;
+            pre_valid[h] = nblk < n_blks && row < n;
+            pre_src[h] = pre_valid[h] ? (live ? (int64_t)__ldg(live + row) : row) : 0;
+        }
+    };
+    auto fetch_hop2 = [&](int64_t nblk) {  // everything that is indexed by the sample
+        const uint32_t* fs = reinterpret_cast<const uint32_t*>(feat_save);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t sidx = pre_src[h];
+            pre_ridx[h] = -1;
+            pre_up[h][0] = pre_up[h][1] = pre_up[h][2] = 0.f;
+            if (pre_valid[h]) {
+                if (smp.ray_idx) {
+                    pre_ridx[h] = __ldg(smp.ray_idx + sidx);
+                    pre_t[h] = __ldg(smp.ts + sidx);
+                }
+                if (q == 0) {
+                    pre_up[h][0] = __ldg(dL_dsigmas + sidx);
+                    pre_up[h][1] = __ldg(dL_drgbs + 3 * sidx);
+                    pre_up[h][2] = __ldg(dL_drgbs + 3 * sidx + 1);
+                } else if (q == 1) {
+                    pre_up[h][1] = __ldg(dL_drgbs + 3 * sidx + 2);
+                }
+            }
+            // this lane's four words of the row out of the forward's fragment-order save (word x/z = row g, y/w = row g+8 of
+            // the 16-row tile that holds the sample)
+            const int64_t t2 = (sidx >> 4) * 2;
+            const int r = (int)(sidx & 15);
+            const int64_t w0 = (r & 7) * 4 + q;
+            const int sub = r >> 3;
+#pragma unroll
+            for (int kt = 0; kt < 2; ++kt) {
+                const uint32_t* p = fs + ((t2 + kt) * 32 + w0) * 4 + sub;
+                pre_feat[kt][h] = pre_valid[h] ? __ldg(p) : 0u;
+                pre_feat[kt][2 + h] = pre_valid[h] ? __ldg(p + 2) : 0u;
+            }
+        }
+        (void)nblk;
+    };
+    if (!issuer) {
+        fetch_hop1(S.blk[0]);
+        fetch_hop2(S.blk[0]);
+    }
+
     // wait until the most recent MMA batch that read dbuf[b] (and everything issued before it) has completed
     auto wait_buf = [&](int b) {
         if (commits[b]) mbar_wait(&S.done[b], (commits[b] - 1u) & 1u);
@@ -1125,61 +1180,45 @@ k_ngp_bwd3(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_
         }
 
         // ================= row warps =================
+        // The rows of THIS block were fetched while the previous block was processed (hop 1: live index, right after that
+        // block's barrier; hop 2: ray index, t, upstream gradients, saved features, half-way through it), so only the last
+        // hop -- the ray's origin and direction, L1/L2 hits shared by the rays' consecutive samples -- is on the critical
+        // path here. (Three dependent global loads at the top of every block were 15 % of the stall samples.)
         const int64_t mtile = blk * B3_WARPS + warp;
         const int64_t base = mtile * 16;
         bool valid[2];
-        float up_sig[2] = {0.f, 0.f}, up_c0[2] = {0.f, 0.f}, up_c1[2] = {0.f, 0.f};
+        float up_sig[2], up_c0[2], up_c1[2];
         SampleIn sm[2];
-        int64_t src[2];
+        uint32_t featA[1][2][4];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int64_t row = base + g + 8 * h;
-            valid[h] = row < n;
-            src[h] = valid[h] ? (live ? (int64_t)__ldg(live + row) : row) : 0;
-            sm[h] = load_sample(smp, src[h], valid[h]);
-            if (valid[h]) {
-                if (q == 0) {
-                    up_sig[h] = __ldg(dL_dsigmas + src[h]);
-                    up_c0[h] = __ldg(dL_drgbs + 3 * src[h]);
-                    up_c1[h] = __ldg(dL_drgbs + 3 * src[h] + 1);
-                } else if (q == 1) {
-                    up_c0[h] = __ldg(dL_drgbs + 3 * src[h] + 2);
-                }
-            }
-        }
-        uint32_t featA[1][2][4];
-        if (live) {
-            const uint32_t* fs = reinterpret_cast<const uint32_t*>(feat_save);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int64_t t2 = (src[h] >> 4) * 2;
-                const int r = (int)(src[h] & 15);
-                const int64_t w0 = (r & 7) * 4 + q;
-                const int sub = r >> 3;
-#pragma unroll
-                for (int kt = 0; kt < 2; ++kt) {
-                    const uint32_t* p = fs + ((t2 + kt) * 32 + w0) * 4 + sub;
-                    featA[0][kt][h] = valid[h] ? __ldg(p) : 0u;
-                    featA[0][kt][2 + h] = valid[h] ? __ldg(p + 2) : 0u;
-                }
-            }
-        } else if (base < n) {
+            valid[h] = pre_valid[h];
+            up_sig[h] = pre_up[h][0]; up_c0[h] = pre_up[h][1]; up_c1[h] = pre_up[h][2];
 #pragma unroll
             for (int kt = 0; kt < 2; ++kt) {
-                const uint4 v = __ldg(feat_save + (mtile * 2 + kt) * 32 + lane);
-                featA[0][kt][0] = v.x; featA[0][kt][1] = v.y; featA[0][kt][2] = v.z; featA[0][kt][3] = v.w;
+                featA[0][kt][h] = pre_feat[kt][h];
+                featA[0][kt][2 + h] = pre_feat[kt][2 + h];
             }
-        } else {
-#pragma unroll
-            for (int kt = 0; kt < 2; ++kt)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) featA[0][kt][e] = 0u;
+            if (valid[h] && pre_ridx[h] >= 0) {
+                const int r = pre_ridx[h];
+                const float t = pre_t[h];
+                sm[h].dx = __ldg(smp.rays_d + 3 * r); sm[h].dy = __ldg(smp.rays_d + 3 * r + 1); sm[h].dz = __ldg(smp.rays_d + 3 * r + 2);
+                sm[h].x = __fmaf_rn(sm[h].dx, t, __ldg(smp.rays_o + 3 * r));
+                sm[h].y = __fmaf_rn(sm[h].dy, t, __ldg(smp.rays_o + 3 * r + 1));
+                sm[h].z = __fmaf_rn(sm[h].dz, t, __ldg(smp.rays_o + 3 * r + 2));
+            } else {
+                bool v = valid[h];
+                sm[h] = load_sample(smp, pre_src[h], v);  // (xyzs / dirs layout, or an invalid row)
+                valid[h] = v;
+            }
         }
         // the previous block's GEMMs still read feat / hid / rin / r1 / r2: its last batch (W1d, buffer 0) completes after
         // every earlier one (the MMAs of one thread complete in order). The CTA barrier also publishes the next ticket and
         // keeps a fast thread from arriving on a `staged` barrier whose previous phase is still open.
         wait_buf(0);
         __syncthreads();
+        const int64_t nblk = S.blk[(it + 1) & 1];  // published by the barrier
+        fetch_hop1(nblk);
 
         // ---- forward recompute, staging each activation as soon as it exists ----
         stage_canon<2>(S.feat, 32, row0, featA[0], g, q);
@@ -1272,6 +1311,7 @@ k_ngp_bwd3(const NgpNet net, const NgpSamples smp, const float* __restrict__ dL_
             load_canon<4>(S.r1, 64, row0, act, g, q);
             relu_bwd_to_frag<1, 64>(c, act, dA);
         }
+        fetch_hop2(nblk);  // the next block's live indices have long arrived
         // ---- layer rgb-1 : dW1r[out 64][in 32] = dr1^T rin ; buffer 0 ; only the h half of its input needs a gradient ----
         wait_buf(0);
         stage_canon<4>(S.dbuf[0], 64, row0, dA[0], g, q);
