@@ -30,6 +30,12 @@ int ngp_abi_version(void); /* == NGP_ABI_VERSION of the header the caller was bu
  * `gpu_launches`; no reference counterpart. */
 unsigned long long ngp_launch_count(void);
 
+/* Debugging aid (tools/step_timeline.py; no reference counterpart): install a device buffer of 2 + 2*capacity uint64
+ * (buf[0] = 0, buf[1] = capacity, written by the caller) and the training-step entry points enqueue a one-thread kernel
+ * after each of their kernels that appends {id, %globaltimer ns}. Recorded into CUDA graphs like any other launch, so
+ * install it before capturing; NULL turns it off (the default). */
+int ngp_trace_set(void* buf);
+
 /* ----------------------------------------------------------------------------------------------
  * The twelve vren operators
  * -------------------------------------------------------------------------------------------- */
@@ -355,6 +361,16 @@ int ngp_update_density_grid(const NgpNet* net, float* density_grid /* (cascades,
                             const float* count_grid /* (cascades, G^3) camera coverage for `erode`, or NULL */,
                             int cascades, int grid_size, float scale, float density_threshold, int warmup, float decay,
                             uint32_t seed, void* workspace, size_t workspace_bytes, void* stream);
+/* The same refresh in two halves, ngp_update_density_grid == pick then eval on one stream. `pick` needs only the OLD grid
+ * and the seed (which cells, sorted in Morton order, and the jittered point in each; clears the scratch grid), so a trainer
+ * runs it on a side stream any time after the previous refresh and only `eval` (density at the points, merge, threshold,
+ * bitfield) sits between two training steps. Both halves must see the same workspace, cascades, grid_size, threshold and
+ * warmup, and nothing else may touch the workspace in between. */
+int ngp_update_density_grid_pick(const float* density_grid, int cascades, int grid_size, float scale, float density_threshold,
+                                 int warmup, uint32_t seed, void* workspace, size_t workspace_bytes, void* stream);
+int ngp_update_density_grid_eval(const NgpNet* net, float* density_grid, uint8_t* density_bitfield, const float* count_grid,
+                                 int cascades, int grid_size, float density_threshold, int warmup, float decay, void* workspace,
+                                 size_t workspace_bytes, void* stream);
 
 /* ----------------------------------------------------------------------------------------------
  * Fused inference path: render(..., test_time=True) (reference models/rendering.py:46-118) as a

@@ -111,6 +111,7 @@ _sz = C.c_size_t
 SIGNATURES = {
     "ngp_abi_version": (_i, []),
     "ngp_launch_count": (C.c_ulonglong, []),
+    "ngp_trace_set": (_i, [_P]),
     "ngp_ray_aabb_intersect": (_i, [_P, _P, _P, _P, _i, _i, _i, _P, _P, _P, _P]),
     "ngp_ray_sphere_intersect": (_i, [_P, _P, _P, _P, _i, _i, _i, _P, _P, _P, _P]),
     "ngp_packbits": (_i, [_P, _i, _i64, _f, _P, _P, _P]),
@@ -156,6 +157,8 @@ SIGNATURES = {
     "ngp_render_infer_frame": (_i, [C.POINTER(NgpNet), C.POINTER(NgpInferCfg), _P, _P, _P, _P, _P, _P, _P, _P, _sz, _P]),
     "ngp_update_grid_workspace": (_sz, [_i, _i]),
     "ngp_update_density_grid": (_i, [C.POINTER(NgpNet), _P, _P, _P, _i, _i, _f, _f, _i, _f, C.c_uint32, _P, _sz, _P]),
+    "ngp_update_density_grid_pick": (_i, [_P, _i, _i, _f, _f, _i, C.c_uint32, _P, _sz, _P]),
+    "ngp_update_density_grid_eval": (_i, [C.POINTER(NgpNet), _P, _P, _P, _i, _i, _f, _i, _f, _P, _sz, _P]),
 }
 
 _lib = None

@@ -15,6 +15,16 @@
 extern unsigned long long g_ngp_launch_count;
 #define NGP_COUNT_LAUNCHES(k) (__atomic_fetch_add(&g_ngp_launch_count, (unsigned long long)(k), __ATOMIC_RELAXED))
 
+// Debugging aid (tools/step_timeline.py): once a trace buffer is installed with ngp_trace_set(), the training-step entry
+// points enqueue a one-thread kernel after each of their kernels that appends {id, %globaltimer} to it -- recorded into
+// CUDA graphs like any other launch, so install it BEFORE capturing. Off (nullptr) in normal operation.
+extern unsigned long long* g_ngp_trace;
+void ngp_trace_stamp(int id, cudaStream_t st);
+#define NGP_TRACE(id, st)                                    \
+    do {                                                     \
+        if (g_ngp_trace) ngp_trace_stamp((id), (st));        \
+    } while (0)
+
 #define NGP_CHECK_LAUNCH()                                   \
     do {                                                     \
         NGP_COUNT_LAUNCHES(1);                               \

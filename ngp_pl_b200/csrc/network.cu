@@ -16,6 +16,24 @@ extern "C" int ngp_abi_version(void) { return NGP_ABI_VERSION; }
 unsigned long long g_ngp_launch_count = 0;
 extern "C" unsigned long long ngp_launch_count(void) { return __atomic_load_n(&g_ngp_launch_count, __ATOMIC_RELAXED); }
 
+// ---- step timeline (debugging aid, see common.cuh) -------------------------------------------------------------------
+unsigned long long* g_ngp_trace = nullptr;
+__global__ void k_trace_stamp(unsigned long long* buf, int id) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned long long i = atomicAdd(&buf[0], 1ull);
+    if (i < buf[1]) {
+        buf[2 + 2 * i] = (unsigned long long)id;
+        buf[3 + 2 * i] = t;
+    }
+}
+void ngp_trace_stamp(int id, cudaStream_t st) { k_trace_stamp<<<1, 1, 0, st>>>(g_ngp_trace, id); }
+// buf: device array of 2 + 2 * capacity u64, buf[0] = 0 (cursor) and buf[1] = capacity set by the caller; nullptr = off
+extern "C" int ngp_trace_set(void* buf) {
+    g_ngp_trace = (unsigned long long*)buf;
+    return 0;
+}
+
 // -------------------------------------------------------------------------------------------------
 // host: level table (tiny-cuda-nn GridEncoding constructor semantics)
 // -------------------------------------------------------------------------------------------------
@@ -384,6 +402,7 @@ extern "C" int ngp_net_forward(const NgpNet* net, const NgpSamples* smp, int wan
         default: launch_fwd<1, 256, 2>(net, smp, want_rgb, sigmas, rgbs, h_out, feat_save, st); break;  // 16 samples/warp, 16 warps/SM
     }
     NGP_CHECK_LAUNCH();
+    NGP_TRACE(3, st);
     return 0;
 }
 
@@ -1557,6 +1576,7 @@ extern "C" int ngp_net_backward_mlp(const NgpNet* net, const NgpSamples* smp, co
             n_mtiles * 16, sched);
     }
     NGP_CHECK_LAUNCH();
+    NGP_TRACE(6, (cudaStream_t)stream);
     return 0;
 }
 
@@ -1574,6 +1594,7 @@ extern "C" int ngp_net_backward_scatter(const NgpNet* net, const NgpSamples* smp
     k_grid_scatter_merged<<<(unsigned)gx, SCATTER_THREADS, 0, (cudaStream_t)stream>>>(
         *net, *smp, (const uint32_t*)workspace, n_mtiles * 16, loss_scale, grad_enc + NGP_DENSITY_MLP_PARAMS);
     NGP_CHECK_LAUNCH();
+    NGP_TRACE(7, (cudaStream_t)stream);
     return 0;
 }
 

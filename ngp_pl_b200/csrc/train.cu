@@ -6,6 +6,7 @@
 #include "march.cuh"
 #include "composite.cuh"
 #include "../../include/ngp_b200.h"
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
 
@@ -170,6 +171,7 @@ extern "C" int ngp_render_train_march(const NgpTrainCfg* cfg, const NgpTrainBuff
     else NGP_LAUNCH_MARCH(false, false);
 #undef NGP_LAUNCH_MARCH
     NGP_CHECK_LAUNCH();
+    NGP_TRACE(2, st);
     return 0;
 }
 
@@ -288,6 +290,20 @@ __global__ void k_train_grad_scale(float* __restrict__ scalars, int* __restrict_
 // depends on that ray's composited colour / opacity only): k_train_composite_fw + k_nerf_loss_grad + k_train_composite_bw
 // without the two extra launches and with the second sweep over the ray's samples hitting L1/L2.
 #define CL_WARPS 8  // rays per block of k_train_composite_loss
+#define CL_CACHE 8  // trips (of 32 samples) of a ray held in registers between the forward and the backward sweep
+struct CLSample {
+    float sg, de, ti;
+    float3 c;
+};
+__device__ __forceinline__ CLSample cl_load(const float* __restrict__ sg, const float* __restrict__ dl,
+                                            const float* __restrict__ tt, const float* __restrict__ cl, int i) {
+    CLSample x;
+    x.sg = __ldg(sg + i);
+    x.de = __ldg(dl + i);
+    x.ti = __ldg(tt + i);
+    x.c = make_float3(__ldg(cl + 3 * i), __ldg(cl + 3 * i + 1), __ldg(cl + 3 * i + 2));
+    return x;
+}
 __global__ void __launch_bounds__(CL_WARPS * 32) k_train_composite_loss(const NgpTrainCfg cfg, const int* __restrict__ n_samples, const int* __restrict__ offsets,
                                        const float* __restrict__ sigmas, const float* __restrict__ rgbs,
                                        const float* __restrict__ deltas, const float* __restrict__ ts,
@@ -309,11 +325,60 @@ __global__ void __launch_bounds__(CL_WARPS * 32) k_train_composite_loss(const Ng
     const float* dl = deltas + start;
     const float* tt = ts + start;
     const float* cl = rgbs + 3 * start;
-    const CompositeOut o = composite_ray_warp(
-        n, cfg.T_threshold, lane,
-        [&](int i) { return __ldg(sg + i); }, [&](int i) { return __ldg(dl + i); }, [&](int i) { return __ldg(tt + i); },
-        [&](int i) { return make_float3(__ldg(cl + 3 * i), __ldg(cl + 3 * i + 1), __ldg(cl + 3 * i + 2)); },
-        [&](int, float) {});
+    // The ray's first CL_CACHE trips of 32 samples are loaded up front (independent loads, one exposed latency instead of
+    // one per trip) and kept in registers for the backward sweep; longer rays continue trip by trip from memory. The
+    // kernel is one wave of warps and lasts as long as its longest ray: with the generic helpers (a dependent load ->
+    // scan chain per trip, twice) that was 24 us (profiles/r02_step_timeline_n1.txt). Arithmetic and its order are those of
+    // composite_ray_warp / composite_ray_warp_bwd (composite.cuh), minus the depth and ws scans whose gradients are zero.
+    CLSample sm[CL_CACHE];
+#pragma unroll
+    for (int k = 0; k < CL_CACHE; ++k) {
+        const int i = k * 32 + lane;
+        sm[k].sg = 0.f; sm[k].de = 0.f; sm[k].ti = 0.f; sm[k].c = make_float3(0.f, 0.f, 0.f);
+        if (i < n) sm[k] = cl_load(sg, dl, tt, cl, i);
+    }
+    CompositeOut o;
+    {
+        float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_d = 0.f, acc_o = 0.f, T_carry = 1.0f;
+        int n_comp = 0;
+        bool done = false;
+        auto trip = [&](int base, const CLSample& x) {
+            const int i = base + lane;
+            const bool valid = i < n;
+            const float a = valid ? 1.0f - __expf(-(x.sg * x.de)) : 0.f;
+            const float T_inc = warp_scan_mul(1.0f - a, lane) * T_carry;
+            float T_exc = __shfl_up_sync(0xffffffffu, T_inc, 1);
+            if (lane == 0) T_exc = T_carry;
+            const bool comp = valid && (i == 0 || T_exc > cfg.T_threshold);
+            const float w = comp ? a * T_exc : 0.f;
+            if (comp) {
+                acc_r = fmaf(w, x.c.x, acc_r);
+                acc_g = fmaf(w, x.c.y, acc_g);
+                acc_b = fmaf(w, x.c.z, acc_b);
+                acc_d = fmaf(w, x.ti, acc_d);
+                acc_o += w;
+            }
+            n_comp += __popc(__ballot_sync(0xffffffffu, comp));
+            done = __ballot_sync(0xffffffffu, valid && !(T_inc > cfg.T_threshold)) != 0u;
+            T_carry = __shfl_sync(0xffffffffu, T_inc, 31);
+        };
+#pragma unroll
+        for (int k = 0; k < CL_CACHE; ++k)
+            if (k * 32 < n && !done) trip(k * 32, sm[k]);
+        for (int base = CL_CACHE * 32; base < n && !done; base += 32) {
+            CLSample x;
+            x.sg = 0.f; x.de = 0.f; x.ti = 0.f; x.c = make_float3(0.f, 0.f, 0.f);
+            if (base + lane < n) x = cl_load(sg, dl, tt, cl, base + lane);
+            trip(base, x);
+        }
+        o.r = warp_sum(acc_r);
+        o.g = warp_sum(acc_g);
+        o.b = warp_sum(acc_b);
+        o.depth = warp_sum(acc_d);
+        o.opacity = warp_sum(acc_o);
+        o.n_composited = n_comp;
+        o.total_samples = done ? n_comp - 1 : n_comp;
+    }
     const float rest = 1.0f - o.opacity;  // rgb += bg * (1 - opacity), reference rendering.py:160-161
     const float3 out = make_float3(o.r + bg[0] * rest, o.g + bg[1] * rest, o.b + bg[2] * rest);
     // NeRFLoss (reference losses.py:47-60, lambda_distortion = 0) and its per-ray gradients
@@ -334,19 +399,57 @@ __global__ void __launch_bounds__(CL_WARPS * 32) k_train_composite_loss(const Ng
         const float dO = cfg.lambda_opacity * (-lg - 1.0f) * inv_n - (dC.x * bg[0] + dC.y * bg[1] + dC.z * bg[2]);
         float* ds = dsigmas + start;
         float* dc = drgbs + 3 * start;
-        n_comp = composite_ray_warp_bwd(
-            n, cfg.T_threshold, lane, dO, 0.f, dC, o.opacity, o.depth, make_float3(o.r, o.g, o.b),
-            [&](int i) { return __ldg(sg + i); }, [&](int i) { return __ldg(dl + i); }, [&](int i) { return __ldg(tt + i); },
-            [&](int i) { return make_float3(__ldg(cl + 3 * i), __ldg(cl + 3 * i + 1), __ldg(cl + 3 * i + 2)); },
-            [&](int) { return 0.f; }, [&](int) { return 0.f; },
-            [&](int i, float v) {
-                ds[i] = v;
-                m = fmaxf(m, fabsf(v * fminf(__ldg(sg + i), 3.2690173e6f)));
-            },
-            [&](int i, float3 v) {
-                dc[3 * i] = v.x; dc[3 * i + 1] = v.y; dc[3 * i + 2] = v.z;
-                m = fmaxf(m, fmaxf(fabsf(v.x), fmaxf(fabsf(v.y), fabsf(v.z))));
-            });
+        const float3 C = make_float3(o.r, o.g, o.b);
+        const float dO_term = dO * (1.0f - o.opacity);
+        float T_carry = 1.0f, pr = 0.f, pg = 0.f, pb = 0.f;
+        bool done = false;
+        auto trip = [&](int base, const CLSample& x) {
+            const int i = base + lane;
+            const bool valid = i < n;
+            const float a = valid ? 1.0f - __expf(-(x.sg * x.de)) : 0.f;
+            const float T_inc = warp_scan_mul(1.0f - a, lane) * T_carry;
+            float T_exc = __shfl_up_sync(0xffffffffu, T_inc, 1);
+            if (lane == 0) T_exc = T_carry;
+            const bool comp = valid && (i == 0 || T_exc > cfg.T_threshold);
+            const float w = comp ? a * T_exc : 0.f;
+            const float r_inc = warp_scan_add(w * x.c.x, lane) + pr;
+            const float g_inc = warp_scan_add(w * x.c.y, lane) + pg;
+            const float b_inc = warp_scan_add(w * x.c.z, lane) + pb;
+            if (valid) {
+                float3 dcv = make_float3(0.f, 0.f, 0.f);
+                float dsv = 0.f;
+                if (comp) {
+                    dcv = make_float3(dC.x * w, dC.y * w, dC.z * w);
+                    const float g = dC.x * (x.c.x * T_inc - (C.x - r_inc)) + dC.y * (x.c.y * T_inc - (C.y - g_inc)) +
+                                    dC.z * (x.c.z * T_inc - (C.z - b_inc)) + dO_term;
+                    dsv = x.de * g;
+                }
+                dc[3 * i] = dcv.x; dc[3 * i + 1] = dcv.y; dc[3 * i + 2] = dcv.z;
+                ds[i] = dsv;
+                m = fmaxf(m, fmaxf(fabsf(dcv.x), fmaxf(fabsf(dcv.y), fabsf(dcv.z))));
+                m = fmaxf(m, fabsf(dsv * fminf(x.sg, 3.2690173e6f)));
+            }
+            n_comp += __popc(__ballot_sync(0xffffffffu, comp));
+            done = __ballot_sync(0xffffffffu, valid && !(T_inc > cfg.T_threshold)) != 0u;
+            T_carry = __shfl_sync(0xffffffffu, T_inc, 31);
+            pr = __shfl_sync(0xffffffffu, r_inc, 31);
+            pg = __shfl_sync(0xffffffffu, g_inc, 31);
+            pb = __shfl_sync(0xffffffffu, b_inc, 31);
+        };
+        int base = 0;
+#pragma unroll
+        for (int k = 0; k < CL_CACHE; ++k)
+            if (k * 32 < n && !done) { trip(k * 32, sm[k]); base = k * 32 + 32; }
+        for (; base >= CL_CACHE * 32 && base < n && !done; base += 32) {
+            CLSample x;
+            x.sg = 0.f; x.de = 0.f; x.ti = 0.f; x.c = make_float3(0.f, 0.f, 0.f);
+            if (base + lane < n) x = cl_load(sg, dl, tt, cl, base + lane);
+            trip(base, x);
+        }
+        for (int i = base + lane; i < n; i += 32) {  // past the terminating trip: zero gradients
+            dc[3 * i] = 0.f; dc[3 * i + 1] = 0.f; dc[3 * i + 2] = 0.f;
+            ds[i] = 0.f;
+        }
         m = warp_max(m);
     }
     // Per-ray sums, the loss-scale maximum and the live-list allocation go through ONE set of atomics per BLOCK (8 rays):
@@ -405,14 +508,17 @@ extern "C" int ngp_render_train_step(const NgpNet* net, const NgpTrainCfg* cfg, 
     cudaStream_t st = (cudaStream_t)stream;
     const int n = cfg->n_rays;
     NgpSamples smp = train_samples(cfg, b);
+    NGP_TRACE(13, st);
     rc = ngp_net_forward(net, &smp, 1, b->sigmas, b->rgbs, nullptr, b->feat_save, stream);
     if (rc) return rc;
     k_train_composite_loss<<<ngp_div_up(n, CL_WARPS), CL_WARPS * 32, 0, st>>>(
         *cfg, b->n_samples, b->offsets, b->sigmas, b->rgbs, b->deltas, b->ts, rgb_gt, b->rgb, b->opacity, b->depth, b->dsigmas,
         b->drgbs, b->scalars, b->live_idx, b->counters, b->bg_dev);
     NGP_CHECK_LAUNCH();
+    NGP_TRACE(4, st);
     k_train_grad_scale<<<1, 1, 0, st>>>(b->scalars, b->counters, 1);
     NGP_CHECK_LAUNCH();
+    NGP_TRACE(5, st);
     if (b->live_idx) {
         smp.live_idx = b->live_idx;
         smp.n_live_dev = b->counters + 5;
@@ -582,9 +688,11 @@ extern "C" int ngp_adam_step(float* params, float* grads, float* exp_avg, float*
         int grid = ngp_div_up((n >> 2) + 1, 256);
         const int cap = ngp_sm_count() * 2;
         if (grid > cap) grid = cap;
+        NGP_TRACE(18, st);
         k_adam<<<grid, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, (__half*)params_half, n, lr_dev, step_dev, beta1,
                                       beta2, eps, grad_mul);
         NGP_CHECK_LAUNCH();
+        NGP_TRACE(8, st);
     }
     if (increment_step) {
         k_step_inc<<<1, 1, 0, st>>>(step_dev);
@@ -891,12 +999,14 @@ extern "C" int ngp_adam_step_fused(int world, int rank, const uint64_t* peer_gra
 #define NGP_LAUNCH_FUSED(W)                                                                                                \
     k_adam_fused<W><<<grid, 256, 0, st>>>(pp, world, rank, params, exp_avg, exp_avg_sq, lo4, hi4, (float4*)zero_buf,       \
                                           zero_buf ? n4 : 0, sync, lr_dev, step_dev, beta1, beta2, eps, 1.0f / (float)world)
+    NGP_TRACE(18, st);
     if (world <= 2) NGP_LAUNCH_FUSED(2);
     else if (world <= 4) NGP_LAUNCH_FUSED(4);
     else if (world <= 8) NGP_LAUNCH_FUSED(8);
     else NGP_LAUNCH_FUSED(16);
 #undef NGP_LAUNCH_FUSED
     NGP_CHECK_LAUNCH();
+    NGP_TRACE(8, st);
     if (increment_step) {
         k_step_inc<<<1, 1, 0, st>>>(step_dev);
         NGP_CHECK_LAUNCH();
@@ -997,10 +1107,12 @@ extern "C" int ngp_sample_rays(const float* poses, const float* directions, cons
         !rays_d || !rgb_gt || !noise)
         return NGP_EINVAL;
     if (n == 0) return 0;
+    NGP_TRACE(11, (cudaStream_t)stream);
     k_sample_rays<<<ngp_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(poses, directions, images, (uint32_t)n_img,
                                                                          (uint32_t)n_pix, n, seed, stream_id, rng_draw, rays_o,
                                                                          rays_d, rgb_gt, noise);
     NGP_CHECK_LAUNCH();
+    NGP_TRACE(1, (cudaStream_t)stream);
     return 0;
 }
 
@@ -1027,34 +1139,48 @@ __global__ void k_grid_flags(const float* __restrict__ grid, int64_t n, float th
     if (i < n) flags[i] = grid[i] > thr ? 1 : 0;
 }
 
-// Pick the cells to refresh and a jittered point inside each. Slot layout per cascade:
-//   warmup : g3 slots, slot i = Morton index i
-//   else   : 2*M slots, [0,M) uniform random cells, [M,2M) random occupied cells (skipped if none)
-__global__ void k_grid_pick(const GridUpd u, int c, const int* __restrict__ occ_list, const int* __restrict__ occ_count,
-                            int* __restrict__ cell_idx, float* __restrict__ xyz) {
-    const uint32_t n_slots = u.warmup ? u.g3 : 2u * u.M;
+// Pick the cells to refresh. Slot layout per cascade:
+//   warmup : g3 slots, slot i = Morton index i (no pick, no sort)
+//   else   : 2*M slots, [0,M) uniform random cells, [M,2M) random occupied cells (key = g3, "none", if there are none)
+// The picked Morton indices are then SORTED (cub radix sort) before the density is evaluated: the result of the refresh does
+// not depend on the order the cells are evaluated in (it is scattered back per cell), but the evaluation does -- 1M cells in
+// random order make every hash-grid gather of a warp hit 32 different sectors and the density pass took 368 us; in Morton
+// order neighbouring threads share cells on the coarse levels, like consecutive samples of a ray do (profiles/
+// r02_step_timeline_n1.txt).
+__global__ void k_grid_pick_cells(const GridUpd u, int c, const int* __restrict__ occ_list, const int* __restrict__ occ_count,
+                                  uint32_t* __restrict__ keys) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_slots) return;
-    uint32_t h = pcg_hash(u.seed ^ pcg_hash(i + 0x9e3779b9u * (uint32_t)(c + 1)));
-    int idx;
-    if (u.warmup) {
-        idx = (int)i;
-    } else if (i < u.M) {
+    if (i >= 2u * u.M) return;
+    const uint32_t h = pcg_hash(u.seed ^ pcg_hash(i + 0x9e3779b9u * (uint32_t)(c + 1)));
+    uint32_t idx;
+    if (i < u.M) {
         // uniform cell: three independent coordinates, then Morton order (reference networks.py:182-184)
         const uint32_t G = (uint32_t)u.grid_size;
         const uint32_t cx = pcg_hash(h) % G, cy = pcg_hash(h ^ 0x68bc21ebu) % G, cz = pcg_hash(h ^ 0x02e5be93u) % G;
-        idx = (int)morton_encode3(cx, cy, cz);
+        idx = morton_encode3(cx, cy, cz);
     } else {
         const int cnt = *occ_count;
-        if (cnt <= 0) {
-            cell_idx[i] = -1;
-            xyz[3 * i] = 0.f; xyz[3 * i + 1] = 0.f; xyz[3 * i + 2] = 0.f;
-            return;
-        }
-        idx = occ_list[pcg_hash(h ^ 0x7feb352du) % (uint32_t)cnt];
+        idx = cnt <= 0 ? u.g3 : (uint32_t)occ_list[pcg_hash(h ^ 0x7feb352du) % (uint32_t)cnt];
     }
-    cell_idx[i] = idx;
-    const uint32_t m = (uint32_t)idx;
+    keys[i] = idx;
+}
+
+// one jittered point inside each picked cell (keys == nullptr: warm-up, slot i is cell i)
+__global__ void k_grid_jitter(const GridUpd u, int c, const uint32_t* __restrict__ keys, int* __restrict__ cell_idx,
+                              float* __restrict__ xyz) {
+    const uint32_t n_slots = u.warmup ? u.g3 : 2u * u.M;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    const uint32_t m = keys ? keys[i] : i;
+    // a cell picked more than once (the keys are sorted, so its slots are adjacent) is evaluated at its FIRST slot's point
+    // only: the reference's index_put keeps an arbitrary one of the duplicates, this keeps the refresh deterministic
+    if (m >= u.g3 || (keys && i > 0 && keys[i - 1] == m)) {
+        cell_idx[i] = -1;
+        xyz[3 * i] = 0.f; xyz[3 * i + 1] = 0.f; xyz[3 * i + 2] = 0.f;
+        return;
+    }
+    cell_idx[i] = (int)m;
+    uint32_t h = pcg_hash(u.seed ^ pcg_hash(i + 0x9e3779b9u * (uint32_t)(c + 1)));
     const float G1 = (float)(u.grid_size - 1);
     const float s = fminf(scalbnf(1.0f, c - 1), u.scale);
     const float half_cell = s / (float)u.grid_size;
@@ -1068,12 +1194,13 @@ __global__ void k_grid_pick(const GridUpd u, int c, const int* __restrict__ occ_
 }
 
 // tmp[cell] = sigma (duplicates: last writer wins, as with the reference's index_put)
-__global__ void k_grid_scatter(const int* __restrict__ cell_idx, const float* __restrict__ sigma, uint32_t n,
-                               float* __restrict__ tmp) {
+// slots are cascade-major (n_slots per cascade); cell_idx is the cell inside its cascade
+__global__ void k_grid_scatter(const int* __restrict__ cell_idx, const float* __restrict__ sigma, uint32_t n_slots,
+                               uint32_t n_all, uint32_t g3, float* __restrict__ tmp) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n_all) return;
     const int c = cell_idx[i];
-    if (c >= 0) tmp[c] = sigma[i];
+    if (c >= 0) tmp[(size_t)(i / n_slots) * g3 + (uint32_t)c] = sigma[i];
 }
 
 // grid = grid < 0 ? grid : max(grid*decay, tmp); accumulate sum / count of the positive cells
@@ -1090,11 +1217,21 @@ __global__ void k_grid_merge(float* __restrict__ grid, const float* __restrict__
         grid[i] = g;
         if (g > 0.f) { s += g; cnt += 1.f; }
     }
+    // one pair of atomics per BLOCK: ~9.5k warps adding to the same two addresses serialised in L2 and cost more than the
+    // 24 MB this kernel streams
+    __shared__ float sh_s[8], sh_c[8];
     s = warp_sum(s);
     cnt = warp_sum(cnt);
     if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&stats[0], s);
-        atomicAdd(&stats[1], cnt);
+        sh_s[threadIdx.x >> 5] = s;
+        sh_c[threadIdx.x >> 5] = cnt;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float bs = 0.f, bc = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { bs += sh_s[w]; bc += sh_c[w]; }
+        atomicAdd(&stats[0], bs);
+        atomicAdd(&stats[1], bc);
     }
 }
 __global__ void k_grid_mean(float* __restrict__ stats) {
@@ -1102,75 +1239,134 @@ __global__ void k_grid_mean(float* __restrict__ stats) {
     stats[2] = stats[0] / stats[1];
 }
 
-// workspace layout (all 256-byte aligned):
-//   tmp (cascades*g3 f32) | flags (g3 u8) | occ_list (g3 i32) | occ_count (i32) | cell_idx (g3 i32)
-//   | xyz (g3*3 f32) | sigma (g3 f32) | stats (4 f32) | cub temp
+// workspace layout (all 256-byte aligned), C = cascades:
+//   tmp (C*g3 f32) | flags (g3 u8) | occ_list (g3 i32) | occ_count (i32) | cell_idx (C*g3 i32, cascade offset included)
+//   | xyz (C*g3*3 f32) | sigma (C*g3 f32) | stats (4 f32) | keys (g3 u32) | keys_sorted (g3 u32) | cub temp
 static size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
-static size_t select_temp_bytes(int g3) {
-    size_t bytes = 0;
-    cub::DeviceSelect::Flagged(nullptr, bytes, cub::CountingInputIterator<int>(0), (const uint8_t*)nullptr, (int*)nullptr,
-                               (int*)nullptr, g3);
-    return al256(bytes);
+static int key_bits(size_t g3) {  // bits of the largest key, g3 ("none")
+    int b = 1;
+    while (((size_t)1 << b) <= g3) ++b;
+    return b;
+}
+static size_t cub_temp_bytes(size_t g3) {
+    size_t sel = 0, srt = 0;
+    cub::DeviceSelect::Flagged(nullptr, sel, cub::CountingInputIterator<int>(0), (const uint8_t*)nullptr, (int*)nullptr,
+                               (int*)nullptr, (int)g3);
+    cub::DeviceRadixSort::SortKeys(nullptr, srt, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)g3, 0, key_bits(g3));
+    return al256(sel > srt ? sel : srt);
+}
+struct GridWs {
+    float* tmp; uint8_t* flags; int* occ_list; int* occ_count; int* cell_idx; float* xyz; float* sigma; float* stats;
+    uint32_t* keys; uint32_t* keys_sorted; void* cub_temp; size_t cub_bytes; size_t total;
+};
+static GridWs grid_ws(void* workspace, int cascades, size_t g3) {
+    GridWs g;
+    char* w = (char*)workspace;
+    const size_t C = (size_t)cascades;
+    g.tmp = (float*)w; w += al256(C * g3 * 4);
+    g.flags = (uint8_t*)w; w += al256(g3);
+    g.occ_list = (int*)w; w += al256(g3 * 4);
+    g.occ_count = (int*)w; w += 256;
+    g.cell_idx = (int*)w; w += al256(C * g3 * 4);
+    g.xyz = (float*)w; w += al256(C * g3 * 12);
+    g.sigma = (float*)w; w += al256(C * g3 * 4);
+    g.stats = (float*)w; w += 256;
+    g.keys = (uint32_t*)w; w += al256(g3 * 4);
+    g.keys_sorted = (uint32_t*)w; w += al256(g3 * 4);
+    g.cub_temp = w;
+    g.cub_bytes = cub_temp_bytes(g3);
+    g.total = (size_t)(w - (char*)workspace) + g.cub_bytes;
+    return g;
 }
 extern "C" size_t ngp_update_grid_workspace(int cascades, int grid_size) {
     if (cascades < 1 || grid_size < 1) return 0;
+    return grid_ws(nullptr, cascades, (size_t)grid_size * grid_size * grid_size).total;
+}
+
+// First half of the refresh: everything that depends on the OLD density grid and the seed but not on the weights -- which
+// cells to re-evaluate (sorted) and a jittered point in each, plus clearing the scratch grid. A trainer runs it on a side
+// stream any time after the previous refresh, so that only the second half sits between two training steps.
+extern "C" int ngp_update_density_grid_pick(const float* density_grid, int cascades, int grid_size, float scale,
+                                            float density_threshold, int warmup, uint32_t seed, void* workspace,
+                                            size_t workspace_bytes, void* stream) {
+    if (!density_grid || !workspace || cascades < 1 || grid_size < 2 || grid_size > 1024) return NGP_EINVAL;
+    if (workspace_bytes < ngp_update_grid_workspace(cascades, grid_size)) return NGP_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
     const size_t g3 = (size_t)grid_size * grid_size * grid_size;
-    return al256(cascades * g3 * 4) + al256(g3) + al256(g3 * 4) + 256 + al256(g3 * 4) + al256(g3 * 12) + al256(g3 * 4) + 256 +
-           select_temp_bytes((int)g3);
+    const GridWs g = grid_ws(workspace, cascades, g3);
+    size_t cub_bytes = g.cub_bytes;
+    GridUpd u;
+    u.cascades = cascades; u.grid_size = grid_size; u.warmup = warmup ? 1 : 0;
+    u.g3 = (uint32_t)g3; u.M = (uint32_t)(g3 / 4); u.scale = scale; u.seed = seed;
+    NGP_CUDA(cudaMemsetAsync(g.tmp, 0, cascades * g3 * 4, st));
+    NGP_CUDA(cudaMemsetAsync(g.stats, 0, 16, st));
+    NGP_COUNT_LAUNCHES(2);
+    NGP_TRACE(20, st);
+    const uint32_t n_slots = warmup ? (uint32_t)g3 : 2u * u.M;
+    for (int c = 0; c < cascades; ++c) {
+        if (!warmup) {
+            k_grid_flags<<<ngp_div_up(g3, 256), 256, 0, st>>>(density_grid + c * g3, (int64_t)g3, density_threshold, g.flags);
+            NGP_CHECK_LAUNCH();
+            NGP_CUDA(cub::DeviceSelect::Flagged(g.cub_temp, cub_bytes, cub::CountingInputIterator<int>(0), g.flags, g.occ_list,
+                                                g.occ_count, (int)g3, st));
+            NGP_COUNT_LAUNCHES(2);  // cub: init + sweep kernels
+            NGP_TRACE(21, st);
+            k_grid_pick_cells<<<ngp_div_up(n_slots, 256), 256, 0, st>>>(u, c, g.occ_list, g.occ_count, g.keys);
+            NGP_CHECK_LAUNCH();
+            NGP_CUDA(cub::DeviceRadixSort::SortKeys(g.cub_temp, cub_bytes, (const uint32_t*)g.keys, g.keys_sorted, (int)n_slots,
+                                                    0, key_bits(g3), st));
+            NGP_COUNT_LAUNCHES(2 + (key_bits(g3) + 7) / 8);  // cub onesweep: histogram + scan + one kernel per 8-bit digit
+        }
+        k_grid_jitter<<<ngp_div_up(n_slots, 256), 256, 0, st>>>(u, c, warmup ? nullptr : g.keys_sorted,
+                                                                g.cell_idx + (size_t)c * n_slots, g.xyz + 3 * (size_t)c * n_slots);
+        NGP_CHECK_LAUNCH();
+        NGP_TRACE(22, st);
+    }
+    return 0;
+}
+
+// Second half: the density at the picked points (ONE pass over the slots of all cascades), the merge and the bitfield.
+extern "C" int ngp_update_density_grid_eval(const NgpNet* net, float* density_grid, uint8_t* density_bitfield,
+                                            const float* count_grid, int cascades, int grid_size, float density_threshold,
+                                            int warmup, float decay, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!net || !density_grid || !density_bitfield || !workspace || cascades < 1 || grid_size < 2 || grid_size > 1024)
+        return NGP_EINVAL;
+    if (workspace_bytes < ngp_update_grid_workspace(cascades, grid_size)) return NGP_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t g3 = (size_t)grid_size * grid_size * grid_size;
+    const GridWs g = grid_ws(workspace, cascades, g3);
+    const size_t n_slots = warmup ? g3 : 2 * (g3 / 4);
+    const size_t n_all = n_slots * (size_t)cascades;
+    NgpSamples smp;
+    smp.xyzs = g.xyz; smp.dirs = nullptr; smp.rays_o = nullptr; smp.rays_d = nullptr; smp.ray_idx = nullptr; smp.ts = nullptr;
+    smp.n = (int64_t)n_all; smp.n_dev = nullptr; smp.live_idx = nullptr; smp.n_live_dev = nullptr;
+    int rc = ngp_net_forward(net, &smp, 0, g.sigma, nullptr, nullptr, nullptr, stream);
+    if (rc) return rc;
+    k_grid_scatter<<<ngp_div_up(n_all, 256), 256, 0, st>>>(g.cell_idx, g.sigma, (uint32_t)n_slots, (uint32_t)n_all, (uint32_t)g3,
+                                                           g.tmp);
+    NGP_CHECK_LAUNCH();
+    NGP_TRACE(23, st);
+    int grid = ngp_div_up((int64_t)cascades * g3, 256);
+    if (grid > ngp_sm_count() * 8) grid = ngp_sm_count() * 8;
+    k_grid_merge<<<grid, 256, 0, st>>>(density_grid, g.tmp, (int64_t)cascades * g3, decay, count_grid, g.stats);
+    NGP_CHECK_LAUNCH();
+    k_grid_mean<<<1, 1, 0, st>>>(g.stats);
+    NGP_CHECK_LAUNCH();
+    NGP_TRACE(24, st);
+    // threshold = min(mean, density_threshold) evaluated on the device (fminf ignores a NaN mean)
+    rc = ngp_packbits(density_grid, 0, (int64_t)cascades * g3 / 8, density_threshold, g.stats + 2, density_bitfield, stream);
+    NGP_TRACE(25, st);
+    return rc;
 }
 
 extern "C" int ngp_update_density_grid(const NgpNet* net, float* density_grid, uint8_t* density_bitfield,
                                        const float* count_grid, int cascades, int grid_size, float scale,
                                        float density_threshold, int warmup, float decay, uint32_t seed, void* workspace,
                                        size_t workspace_bytes, void* stream) {
-    if (!net || !density_grid || !density_bitfield || !workspace || cascades < 1 || grid_size < 2 || grid_size > 1024)
-        return NGP_EINVAL;
-    if (workspace_bytes < ngp_update_grid_workspace(cascades, grid_size)) return NGP_EINVAL;
-    cudaStream_t st = (cudaStream_t)stream;
-    const size_t g3 = (size_t)grid_size * grid_size * grid_size;
-    char* w = (char*)workspace;
-    float* tmp = (float*)w; w += al256(cascades * g3 * 4);
-    uint8_t* flags = (uint8_t*)w; w += al256(g3);
-    int* occ_list = (int*)w; w += al256(g3 * 4);
-    int* occ_count = (int*)w; w += 256;
-    int* cell_idx = (int*)w; w += al256(g3 * 4);
-    float* xyz = (float*)w; w += al256(g3 * 12);
-    float* sigma = (float*)w; w += al256(g3 * 4);
-    float* stats = (float*)w; w += 256;
-    void* cub_temp = w;
-    size_t cub_bytes = select_temp_bytes((int)g3);
-
-    GridUpd u;
-    u.cascades = cascades; u.grid_size = grid_size; u.warmup = warmup ? 1 : 0;
-    u.g3 = (uint32_t)g3; u.M = (uint32_t)(g3 / 4); u.scale = scale; u.seed = seed;
-    NGP_CUDA(cudaMemsetAsync(tmp, 0, cascades * g3 * 4, st));
-    NGP_CUDA(cudaMemsetAsync(stats, 0, 16, st));
-    NGP_COUNT_LAUNCHES(2);
-    const uint32_t n_slots = warmup ? (uint32_t)g3 : 2u * u.M;
-    for (int c = 0; c < cascades; ++c) {
-        if (!warmup) {
-            k_grid_flags<<<ngp_div_up(g3, 256), 256, 0, st>>>(density_grid + c * g3, (int64_t)g3, density_threshold, flags);
-            NGP_CHECK_LAUNCH();
-            NGP_CUDA(cub::DeviceSelect::Flagged(cub_temp, cub_bytes, cub::CountingInputIterator<int>(0), flags, occ_list,
-                                                occ_count, (int)g3, st));
-            NGP_COUNT_LAUNCHES(2);  // cub: init + sweep kernels
-        }
-        k_grid_pick<<<ngp_div_up(n_slots, 256), 256, 0, st>>>(u, c, occ_list, occ_count, cell_idx, xyz);
-        NGP_CHECK_LAUNCH();
-        NgpSamples smp;
-        smp.xyzs = xyz; smp.dirs = nullptr; smp.rays_o = nullptr; smp.rays_d = nullptr; smp.ray_idx = nullptr; smp.ts = nullptr;
-        smp.n = n_slots; smp.n_dev = nullptr; smp.live_idx = nullptr; smp.n_live_dev = nullptr;
-        int rc = ngp_net_forward(net, &smp, 0, sigma, nullptr, nullptr, nullptr, stream);
-        if (rc) return rc;
-        k_grid_scatter<<<ngp_div_up(n_slots, 256), 256, 0, st>>>(cell_idx, sigma, n_slots, tmp + c * g3);
-        NGP_CHECK_LAUNCH();
-    }
-    int grid = ngp_div_up((int64_t)cascades * g3, 256);
-    if (grid > ngp_sm_count() * 8) grid = ngp_sm_count() * 8;
-    k_grid_merge<<<grid, 256, 0, st>>>(density_grid, tmp, (int64_t)cascades * g3, decay, count_grid, stats);
-    NGP_CHECK_LAUNCH();
-    k_grid_mean<<<1, 1, 0, st>>>(stats);
-    NGP_CHECK_LAUNCH();
-    // threshold = min(mean, density_threshold) evaluated on the device (fminf ignores a NaN mean)
-    return ngp_packbits(density_grid, 0, (int64_t)cascades * g3 / 8, density_threshold, stats + 2, density_bitfield, stream);
+    if (!net || !density_bitfield) return NGP_EINVAL;
+    int rc = ngp_update_density_grid_pick(density_grid, cascades, grid_size, scale, density_threshold, warmup, seed, workspace,
+                                          workspace_bytes, stream);
+    if (rc) return rc;
+    return ngp_update_density_grid_eval(net, density_grid, density_bitfield, count_grid, cascades, grid_size, density_threshold,
+                                        warmup, decay, workspace, workspace_bytes, stream);
 }

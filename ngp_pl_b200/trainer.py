@@ -104,8 +104,11 @@ class Trainer:
                  T_threshold=1e-4, betas=(0.9, 0.999), eps=1e-15, max_total_samples=None, update_interval=16,
                  warmup_steps=256, process_group=None, world_size=1, rank=0, seed=0, materialize_ws=False, ddp="nccl",
                  lambda_distortion=0.0, skip_dead_samples=True, fused_loss=True, random_bg=False, erode=False,
-                 lr_schedule=None):
+                 lr_schedule=None, pick_ahead=True):
         self.model = model
+        self.pick_ahead = pick_ahead
+        self._picked = None
+        self._pick_stream = None
         dev = model.density_bitfield.device
         if dev.type != "cuda":
             raise RuntimeError("ngp_pl_b200.Trainer needs the model on a CUDA device (there is no CPU path)")
@@ -346,9 +349,30 @@ class Trainer:
             torch.cuda.synchronize(self.dev)
             dist.barrier(group=self.pg)
 
+    def _refresh_seed(self, step):
+        return (self.seed * 2654435761 + step * 40503 + 12345) & 0xffffffff
+
+    def _pick_key(self, step, density_threshold, warmup):
+        g = self.model.density_grid
+        return (self._refresh_seed(step), float(density_threshold), bool(warmup), g.data_ptr(), g._version)
+
+    def _launch_pick(self, step, density_threshold, warmup, stream):
+        m = self.model
+        rc = _lib.lib().ngp_update_density_grid_pick(
+            m.density_grid.data_ptr(), m.cascades, m.grid_size, float(m.scale), float(density_threshold), int(bool(warmup)),
+            self._refresh_seed(step), self.grid_ws.data_ptr(), self.grid_ws.numel(), stream.cuda_stream)
+        _lib.check(rc, "update_density_grid_pick")
+
     def update_density_grid(self, density_threshold=0.01 * MAX_SAMPLES / 3 ** 0.5, warmup=False, decay=0.95, erode=None):
         """device-side equivalent of NGP.update_density_grid (reference networks.py:240-269); no host sync.
-        erode (default: the constructor's): per-cell decay from model.count_grid (mark_invisible_cells), networks.py:258-260"""
+        erode (default: the constructor's): per-cell decay from model.count_grid (mark_invisible_cells), networks.py:258-260
+
+        The refresh has a weight-independent half (which cells to re-evaluate -- it reads the OLD grid -- sorted, a jittered
+        point in each: ngp_update_density_grid_pick) and a weight-dependent half (density at those points, merge, threshold,
+        bitfield: ..._eval). With pick_ahead (default) the first half of the NEXT refresh is launched on its own stream as
+        soon as this refresh is done, so that it runs under the training steps in between and only the second half sits
+        between two steps; a pick is reused only if seed, threshold, warm-up flag and the grid tensor (address and torch
+        version counter) are what it was made for, otherwise it is redone in line."""
         m = self.model
         erode = self.erode if erode is None else erode
         count = None
@@ -357,13 +381,32 @@ class Trainer:
                 raise RuntimeError("erode=True needs model.count_grid: call model.mark_invisible_cells(K, poses, img_wh) first")
             count = m.count_grid.data_ptr()
         with torch.cuda.device(self.dev):
-            rc = _lib.lib().ngp_update_density_grid(
+            main = torch.cuda.current_stream(self.dev)
+            key = self._pick_key(self.host_step, density_threshold, warmup)
+            picked, self._picked = self._picked, None
+            if picked is not None:
+                main.wait_event(picked[1])  # also when stale: it may still be writing the workspace
+            if picked is None or picked[0] != key:
+                self._launch_pick(self.host_step, density_threshold, warmup, main)
+            rc = _lib.lib().ngp_update_density_grid_eval(
                 C.byref(self.net), m.density_grid.data_ptr(), m.density_bitfield.data_ptr(), count, m.cascades, m.grid_size,
-                float(m.scale), float(density_threshold), int(bool(warmup)), float(decay),
-                (self.seed * 2654435761 + self.host_step * 40503 + 12345) & 0xffffffff,
-                self.grid_ws.data_ptr(), self.grid_ws.numel(), self._st())
-            _lib.check(rc, "update_density_grid")
+                float(density_threshold), int(bool(warmup)), float(decay), self.grid_ws.data_ptr(), self.grid_ws.numel(),
+                main.cuda_stream)
+            _lib.check(rc, "update_density_grid_eval")
             broadcast_occupancy(m.density_bitfield, self.world_size, self.pg)
+            if self.pick_ahead and not torch.cuda.is_current_stream_capturing():
+                if self._pick_stream is None:
+                    self._pick_stream = torch.cuda.Stream(self.dev)
+                    self.grid_ws.record_stream(self._pick_stream)
+                nxt = self.host_step + self.update_interval
+                warm_next = nxt < self.warmup_steps
+                done = torch.cuda.Event()
+                done.record(main)
+                self._pick_stream.wait_event(done)
+                self._launch_pick(nxt, density_threshold, warm_next, self._pick_stream)
+                ev = torch.cuda.Event()
+                ev.record(self._pick_stream)
+                self._picked = (self._pick_key(nxt, density_threshold, warm_next), ev)
 
     # ---- pieces of one step (all asynchronous) -------------------------------------------------------------
     def attach_bank(self, bank):

@@ -223,3 +223,42 @@ def test_launch_counter_counts_graph_replays():
     torch.cuda.synchronize()
     assert tr.launch_count() - n0 == 10 * per_step
     assert int(_lib.lib().ngp_launch_count()) > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["lego", "mip360"])
+def test_refresh_picked_ahead_equals_refresh_in_line(which):
+    """Trainer(pick_ahead=True) launches the weight-independent half of the NEXT occupancy refresh (cell choice, Morton
+    sort, jitter) on its own stream right after a refresh; the grids and bitfields it produces must be bit-identical to
+    the single-stream refresh, across the warm-up boundary and for several cascades, and a pick made for other arguments
+    (or an older grid) must not be reused."""
+    from ngp_pl_b200 import synth
+    from ngp_pl_b200.trainer import Trainer
+    scene = synth.lego_scene(0) if which == "lego" else synth.mip360_scene(0)
+    out = []
+    for ahead in (True, False):
+        model = make_model(scene, amp=0.3)
+        tr = Trainer(model, n_rays=256, pick_ahead=ahead, warmup_steps=32)
+        grids = []
+        for step in (0, 16, 32, 48, 64):  # warm-up, warm-up, then three regular refreshes
+            tr.host_step = step
+            tr.update_density_grid(warmup=step < tr.warmup_steps)
+            assert (tr._picked is not None) == ahead
+            grids.append((model.density_grid.clone(), model.density_bitfield.clone()))
+        # a refresh the pick was not made for: other step (seed), then a grid written behind the trainer's back
+        tr.host_step = 100
+        tr.update_density_grid(warmup=False)
+        grids.append((model.density_grid.clone(), model.density_bitfield.clone()))
+        tr.host_step = 116
+        model.density_grid[:, :5000] = -1.0  # bumps the tensor's version counter: the pick made from the old grid is stale
+        tr.update_density_grid(warmup=False)
+        torch.cuda.synchronize()
+        assert (model.density_grid[:, :5000] == -1).all()
+        grids.append((model.density_grid.clone(), model.density_bitfield.clone()))
+        out.append(grids)
+    for (ga, ba), (gb, bb) in zip(*out):
+        assert torch.equal(ga, gb)
+        # the threshold is min(mean of the positive cells, thr) and the mean is a float atomicAdd reduction over millions of
+        # cells (order-dependent in its last bits): cells within ~1e-6 of it may flip, here and between any two runs
+        flipped = int(sum((((ba ^ bb).to(torch.int32) >> k) & 1).sum() for k in range(8)))
+        assert flipped <= 1e-4 * ga.numel()
