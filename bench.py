@@ -70,7 +70,7 @@ def parse():
                     help="N>1 gradient exchange. p2p: ONE self-synchronising NVLink kernel (reduce-scatter + sharded Adam + "
                          "all-gather, in-kernel barriers, in the step's CUDA graph); nvls: the same through the NVSwitch multicast "
                          "mapping; p2p_host: round 1's host-barrier variant; zero: NCCL reduce_scatter/all_gather; nccl: "
-                         "all-reduce + full Adam (the reference's DDP). auto = p2p for 2 GPUs, nvls beyond")
+                         "all-reduce + full Adam (the reference's DDP). auto = p2p up to 4 GPUs, nvls beyond")
     return ap.parse_args()
 
 
@@ -385,9 +385,10 @@ def run_b200(args):
     scene = make_scene(args.workload)
     esf = scene.exp_step_factor
     bank = synth.RayBank(scene, n_images=N_TRAIN_IMAGES, device=dev, seed=rank)  # every rank: own images order/sampling
-    # auto: the peer-load kernel for 2 GPUs, the NVSwitch-reduced variant beyond (measured: N=2 0.390 vs 0.425 ms/step,
-    # N=8 0.447 vs 0.431; profiles/r02_bench_n2_*.json, r02_bench_n8_*.json); falls back to p2p without a multicast mapping
-    ddp_mode = args.ddp if args.ddp != "auto" else ("p2p" if world <= 2 else "nvls")
+    # auto: the peer-load kernel up to 4 GPUs, the NVSwitch-reduced variant beyond (measured ms/step p2p vs nvls: N=2 0.390 vs
+    # 0.425, N=4 0.381 vs 0.387, N=8 0.447 vs 0.431; profiles/r02_bench_n2_*.json, r02_exchange_residency.txt,
+    # r02_bench_n8_*.json); falls back to p2p without a multicast mapping
+    ddp_mode = args.ddp if args.ddp != "auto" else ("p2p" if world <= 4 else "nvls")
     tkw = dict(n_rays=n_rays, lr=1e-2, exp_step_factor=esf, bg=(scene.bg,) * 3, process_group=pg, world_size=world, rank=rank, seed=rank)
     model = NGP(scene.scale).to(dev)
     try:

@@ -20,6 +20,15 @@ extern unsigned long long g_ngp_launch_count;
 // CUDA graphs like any other launch, so install it BEFORE capturing. Off (nullptr) in normal operation.
 extern unsigned long long* g_ngp_trace;
 void ngp_trace_stamp(int id, cudaStream_t st);
+__device__ __forceinline__ void trace_mark(unsigned long long* buf, int id) {  // what the stamp kernel does, from inside a kernel
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned long long i = atomicAdd(&buf[0], 1ull);
+    if (i < buf[1]) {
+        buf[2 + 2 * i] = (unsigned long long)id;
+        buf[3 + 2 * i] = t;
+    }
+}
 #define NGP_TRACE(id, st)                                    \
     do {                                                     \
         if (g_ngp_trace) ngp_trace_stamp((id), (st));        \

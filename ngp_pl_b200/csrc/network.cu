@@ -18,15 +18,7 @@ extern "C" unsigned long long ngp_launch_count(void) { return __atomic_load_n(&g
 
 // ---- step timeline (debugging aid, see common.cuh) -------------------------------------------------------------------
 unsigned long long* g_ngp_trace = nullptr;
-__global__ void k_trace_stamp(unsigned long long* buf, int id) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    const unsigned long long i = atomicAdd(&buf[0], 1ull);
-    if (i < buf[1]) {
-        buf[2 + 2 * i] = (unsigned long long)id;
-        buf[3 + 2 * i] = t;
-    }
-}
+__global__ void k_trace_stamp(unsigned long long* buf, int id) { trace_mark(buf, id); }
 void ngp_trace_stamp(int id, cudaStream_t st) { k_trace_stamp<<<1, 1, 0, st>>>(g_ngp_trace, id); }
 // buf: device array of 2 + 2 * capacity u64, buf[0] = 0 (cursor) and buf[1] = capacity set by the caller; nullptr = off
 extern "C" int ngp_trace_set(void* buf) {

@@ -863,12 +863,20 @@ __global__ void __launch_bounds__(256, 3)
 k_adam_fused(const FusedPeers peers, const int world, const int rank, float* __restrict__ p, float* __restrict__ m,
              float* __restrict__ v, const int64_t lo4, const int64_t hi4, float4* __restrict__ zero_buf, const int64_t zero_n4,
              uint32_t* __restrict__ sync, const float* __restrict__ lr_dev, const int* __restrict__ step_dev, float beta1,
-             float beta2, float eps, float grad_mul) {
+             float beta2, float eps, float grad_mul, unsigned long long* __restrict__ trace) {
     __shared__ uint32_t s_e;
+    if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace_mark(trace, 30);  // (debugging aid, see common.cuh)
     // ---- start barrier ----
     if (threadIdx.x == 0) s_e = sync[0] + 1u;  // sync[0] is only written by the last block of the previous call
     __syncthreads();
     const uint32_t e = s_e;
+    // The clear of the next step's gradient buffer is local and needs nobody's permission (its last readers were the peers
+    // of the PREVIOUS exchange, which ended with a barrier): every block but the one that runs the start barrier does its
+    // share first, i.e. while this rank waits for the slowest rank's gradients; block 0 does its share after the barrier.
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (blockIdx.x != 0)
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < zero_n4; i += (int64_t)gridDim.x * blockDim.x)
+            zero_buf[i] = z4;
     if (blockIdx.x == 0) {
         if ((int)threadIdx.x < world) {
             st_release_sys(peers.flags[threadIdx.x] + rank, e);
@@ -876,16 +884,11 @@ k_adam_fused(const FusedPeers peers, const int world, const int rank, float* __r
         }
         __syncthreads();
         if (threadIdx.x == 0) st_release_gpu(&sync[3], e);
+        if (trace && threadIdx.x == 0) trace_mark(trace, 31);
+        for (int64_t i = threadIdx.x; i < zero_n4; i += (int64_t)gridDim.x * blockDim.x) zero_buf[i] = z4;
     } else {
         if (threadIdx.x == 0 && !wait_epoch<false>(&sync[3], e)) sync[2] = 1u;
         __syncthreads();
-    }
-    // the clear of the next step's gradient buffer is local and independent: issue it first so the writes drain
-    // while the peer loads are in flight
-    {
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < zero_n4; i += (int64_t)gridDim.x * blockDim.x)
-            zero_buf[i] = z;
     }
     const int t = *step_dev + 1;
     const float lr = *lr_dev;
@@ -895,20 +898,13 @@ k_adam_fused(const FusedPeers peers, const int world, const int rank, float* __r
     const float inv_sqrt_bc2 = rsqrtf(bc2);
     const uint64_t stream_pol = l2_policy_evict_first();
     const bool mc_in = peers.mc_grads != nullptr, mc_out = peers.mc_params_half != nullptr;
-    for (int64_t i = lo4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < hi4; i += (int64_t)gridDim.x * blockDim.x) {
-        float4 g;
-        if (mc_in) {
-            g = multimem_ld_reduce_f4(peers.mc_grads + 4 * i);
-        } else {
-            g = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 part[W];
-#pragma unroll
-            for (int r = 0; r < W; ++r)
-                if (r < world) part[r] = __ldcg(reinterpret_cast<const float4*>(peers.grads[r]) + i);  // all loads in flight
-#pragma unroll
-            for (int r = 0; r < W; ++r)
-                if (r < world) { g.x += part[r].x; g.y += part[r].y; g.z += part[r].z; g.w += part[r].w; }
-        }
+    // U float4 groups per thread per trip, their remote loads issued back to back before anything waits on them: one
+    // multimem.ld_reduce (or one round of peer loads) per trip made the loop a chain of ~30 NVLink round trips per thread
+    // and the data phase 95 us at N=4 although it moves 12 MB in and 6 MB out per rank (profiles/r02_step_timeline_n4.txt)
+    constexpr int U = W <= 2 ? 4 : (W <= 4 ? 2 : 1);  // peer-load path: U * W float4 in flight per thread
+    constexpr int UM = 4;                             // multimem path: the switch reduces, one float4 per group
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+    auto update = [&](const int64_t i, float4 g) {
         float4 pv = ld_f4_hint(reinterpret_cast<const float4*>(p) + i, stream_pol);
         float4 mv = ld_f4_hint(reinterpret_cast<const float4*>(m) + i, stream_pol);
         float4 vv = ld_f4_hint(reinterpret_cast<const float4*>(v) + i, stream_pol);
@@ -916,7 +912,7 @@ k_adam_fused(const FusedPeers peers, const int world, const int rank, float* __r
         // untouched entries (g = m = v = 0 on every rank): nothing changes, nothing to store or to send (see k_adam)
         if (gp[0] == 0.f && gp[1] == 0.f && gp[2] == 0.f && gp[3] == 0.f && mp[0] == 0.f && mp[1] == 0.f && mp[2] == 0.f &&
             mp[3] == 0.f && vp[0] == 0.f && vp[1] == 0.f && vp[2] == 0.f && vp[3] == 0.f)
-            continue;
+            return;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const float gr = gp[k] * grad_mul;
@@ -937,6 +933,36 @@ k_adam_fused(const FusedPeers peers, const int world, const int rank, float* __r
             for (int r = 0; r < W; ++r)
                 if (r < world) reinterpret_cast<uint2*>(peers.params_half[r])[i] = h;
         }
+    };
+    if (mc_in) {
+        for (int64_t i0 = lo4 + tid; i0 < hi4; i0 += nthr * UM) {
+            float4 g[UM];
+#pragma unroll
+            for (int u = 0; u < UM; ++u)
+                if (i0 + u * nthr < hi4) g[u] = multimem_ld_reduce_f4(peers.mc_grads + 4 * (i0 + u * nthr));
+#pragma unroll
+            for (int u = 0; u < UM; ++u)
+                if (i0 + u * nthr < hi4) update(i0 + u * nthr, g[u]);
+        }
+    } else {
+        for (int64_t i0 = lo4 + tid; i0 < hi4; i0 += nthr * U) {
+            float4 part[U][W];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int r = 0; r < W; ++r)
+                    if (r < world && i0 + u * nthr < hi4)
+                        part[u][r] = __ldcg(reinterpret_cast<const float4*>(peers.grads[r]) + i0 + u * nthr);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (i0 + u * nthr >= hi4) break;
+                float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int r = 0; r < W; ++r)
+                    if (r < world) { g.x += part[u][r].x; g.y += part[u][r].y; g.z += part[u][r].z; g.w += part[u][r].w; }
+                update(i0 + u * nthr, g);
+            }
+        }
     }
     // ---- end barrier: last block to finish ----
     __threadfence_system();
@@ -945,11 +971,13 @@ k_adam_fused(const FusedPeers peers, const int world, const int rank, float* __r
         if (atomicAdd(&sync[1], 1u) == gridDim.x - 1u) {
             __threadfence_system();
             sync[1] = 0u;
+            if (trace) trace_mark(trace, 32);
             for (int r = 0; r < world; ++r) st_release_sys(peers.flags[r] + NGP_MAX_PEERS + rank, e);
             for (int r = 0; r < world; ++r)
                 if (!wait_epoch<true>(peers.flags[rank] + NGP_MAX_PEERS + r, e)) sync[2] = 1u;
             sync[0] = e;
             __threadfence();
+            if (trace) trace_mark(trace, 33);
         }
     }
 }
@@ -985,20 +1013,25 @@ extern "C" int ngp_adam_step_fused(int world, int rank, const uint64_t* peer_gra
     int64_t work = hi4 - lo4;
     if (zero_buf && n4 > work) work = n4;
     int grid = ngp_div_up(work > 0 ? work : 1, 256 * 4);
-    // resident blocks per SM: 3 fills the SM's registers (fastest for the kernel alone); NGP_FUSED_BLOCKS_PER_SM (env, read
-    // once) lowers it so that the run-ahead march of the next step can share the SMs while this kernel waits at its barriers
-    static int per_sm = -1;
-    if (per_sm < 0) {
+    // Resident blocks per SM. The kernel is NVLink-bound and spends part of its life waiting at its barriers, and while 3
+    // blocks per SM are resident (80 registers x 768 threads) no block of the next step's run-ahead march fits beside
+    // them. Measured in the pipelined step (profiles/r02_exchange_residency.txt): N=2 3 -> 0.365, 2 -> 0.388, 1 -> 0.443 ms
+    // (half the table per rank: the kernel's own speed wins); N=4 p2p 3 -> 0.3830, 2 -> 0.3807, 1 -> 0.3831 and nvls
+    // 3 -> 0.398, 2 -> 0.387 (the march's share of the SMs wins). NGP_FUSED_BLOCKS_PER_SM (env, read once) overrides.
+    static int per_sm_env = -1;
+    if (per_sm_env < 0) {
         const char* e = getenv("NGP_FUSED_BLOCKS_PER_SM");
-        per_sm = e ? atoi(e) : 3;
-        if (per_sm < 1 || per_sm > 3) per_sm = 3;
+        per_sm_env = e ? atoi(e) : 0;
+        if (per_sm_env < 0 || per_sm_env > 3) per_sm_env = 0;
     }
+    const int per_sm = per_sm_env ? per_sm_env : (world <= 2 ? 3 : 2);
     const int cap = ngp_sm_count() * per_sm;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
 #define NGP_LAUNCH_FUSED(W)                                                                                                \
     k_adam_fused<W><<<grid, 256, 0, st>>>(pp, world, rank, params, exp_avg, exp_avg_sq, lo4, hi4, (float4*)zero_buf,       \
-                                          zero_buf ? n4 : 0, sync, lr_dev, step_dev, beta1, beta2, eps, 1.0f / (float)world)
+                                          zero_buf ? n4 : 0, sync, lr_dev, step_dev, beta1, beta2, eps, 1.0f / (float)world, \
+                                          g_ngp_trace)
     NGP_TRACE(18, st);
     if (world <= 2) NGP_LAUNCH_FUSED(2);
     else if (world <= 4) NGP_LAUNCH_FUSED(4);
