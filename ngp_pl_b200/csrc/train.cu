@@ -1198,21 +1198,27 @@ __global__ void k_grid_pick_cells(const GridUpd u, int c, const int* __restrict_
     keys[i] = idx;
 }
 
-// one jittered point inside each picked cell (keys == nullptr: warm-up, slot i is cell i)
-__global__ void k_grid_jitter(const GridUpd u, int c, const uint32_t* __restrict__ keys, int* __restrict__ cell_idx,
-                              float* __restrict__ xyz) {
-    const uint32_t n_slots = u.warmup ? u.g3 : 2u * u.M;
+// One jittered point inside each picked cell. Warm-up (keys == nullptr): slot i of cascade c is cell i. Otherwise `keys`
+// are this cascade's picked cells sorted AND de-duplicated (*n_keys of them): a cell picked more than once is evaluated once
+// -- the reference's index_put keeps an arbitrary one of the duplicates' values, and with ~150 k occupied cells drawn
+// 524 k times most picks ARE duplicates -- so the density pass runs over the distinct cells only. Slots of successive
+// cascades are appended: tot[c] = first slot of cascade c, tot[cascades] = number of slots of this refresh.
+// cell_idx = c * g3 + cell (-1: nothing to evaluate).
+__global__ void k_grid_jitter(const GridUpd u, int c, const uint32_t* __restrict__ keys, const int* __restrict__ n_keys,
+                              int* __restrict__ tot, int* __restrict__ cell_idx, float* __restrict__ xyz) {
+    const uint32_t n = keys ? (uint32_t)*n_keys : u.g3;
+    const uint32_t base = keys ? (uint32_t)tot[c] : (uint32_t)c * u.g3;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_slots) return;
+    if (i == 0) tot[c + 1] = (int)(base + n);  // read by the next cascade's launch / the second half only
+    if (i >= n) return;
     const uint32_t m = keys ? keys[i] : i;
-    // a cell picked more than once (the keys are sorted, so its slots are adjacent) is evaluated at its FIRST slot's point
-    // only: the reference's index_put keeps an arbitrary one of the duplicates, this keeps the refresh deterministic
-    if (m >= u.g3 || (keys && i > 0 && keys[i - 1] == m)) {
-        cell_idx[i] = -1;
-        xyz[3 * i] = 0.f; xyz[3 * i + 1] = 0.f; xyz[3 * i + 2] = 0.f;
+    const size_t at = (size_t)base + i;
+    if (m >= u.g3) {  // the "no occupied cell" key
+        cell_idx[at] = -1;
+        xyz[3 * at] = 0.f; xyz[3 * at + 1] = 0.f; xyz[3 * at + 2] = 0.f;
         return;
     }
-    cell_idx[i] = (int)m;
+    cell_idx[at] = (int)((uint32_t)c * u.g3 + m);
     uint32_t h = pcg_hash(u.seed ^ pcg_hash(i + 0x9e3779b9u * (uint32_t)(c + 1)));
     const float G1 = (float)(u.grid_size - 1);
     const float s = fminf(scalbnf(1.0f, c - 1), u.scale);
@@ -1222,18 +1228,18 @@ __global__ void k_grid_jitter(const GridUpd u, int c, const uint32_t* __restrict
     for (int k = 0; k < 3; ++k) {
         h = pcg_hash(h + 0x85ebca6bu);
         const float centre = ((float)cc[k] / G1 * 2.0f - 1.0f) * (s - half_cell);
-        xyz[3 * i + k] = centre + (u01(h) * 2.0f - 1.0f) * half_cell;
+        xyz[3 * at + k] = centre + (u01(h) * 2.0f - 1.0f) * half_cell;
     }
 }
 
-// tmp[cell] = sigma (duplicates: last writer wins, as with the reference's index_put)
-// slots are cascade-major (n_slots per cascade); cell_idx is the cell inside its cascade
-__global__ void k_grid_scatter(const int* __restrict__ cell_idx, const float* __restrict__ sigma, uint32_t n_slots,
-                               uint32_t n_all, uint32_t g3, float* __restrict__ tmp) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_all) return;
-    const int c = cell_idx[i];
-    if (c >= 0) tmp[(size_t)(i / n_slots) * g3 + (uint32_t)c] = sigma[i];
+// tmp[cell] = sigma over the first *n_dev slots (n_dev == nullptr: all n_cap); cell_idx = cascade * g3 + cell
+__global__ void k_grid_scatter(const int* __restrict__ cell_idx, const float* __restrict__ sigma, const int* __restrict__ n_dev,
+                               uint32_t n_cap, float* __restrict__ tmp) {
+    const uint32_t n = n_dev ? min((uint32_t)max(*n_dev, 0), n_cap) : n_cap;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = cell_idx[i];
+        if (c >= 0) tmp[c] = sigma[i];
+    }
 }
 
 // grid = grid < 0 ? grid : max(grid*decay, tmp); accumulate sum / count of the positive cells
@@ -1274,7 +1280,8 @@ __global__ void k_grid_mean(float* __restrict__ stats) {
 
 // workspace layout (all 256-byte aligned), C = cascades:
 //   tmp (C*g3 f32) | flags (g3 u8) | occ_list (g3 i32) | occ_count (i32) | cell_idx (C*g3 i32, cascade offset included)
-//   | xyz (C*g3*3 f32) | sigma (C*g3 f32) | stats (4 f32) | keys (g3 u32) | keys_sorted (g3 u32) | cub temp
+//   | xyz (C*g3*3 f32) | sigma (C*g3 f32) | stats (4 f32) | tot (C+1 i32) + n_unique (i32 at [63]) | keys (g3 u32)
+//   | keys_sorted (g3 u32) | cub temp
 static size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 static int key_bits(size_t g3) {  // bits of the largest key, g3 ("none")
     int b = 1;
@@ -1286,10 +1293,14 @@ static size_t cub_temp_bytes(size_t g3) {
     cub::DeviceSelect::Flagged(nullptr, sel, cub::CountingInputIterator<int>(0), (const uint8_t*)nullptr, (int*)nullptr,
                                (int*)nullptr, (int)g3);
     cub::DeviceRadixSort::SortKeys(nullptr, srt, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)g3, 0, key_bits(g3));
+    size_t unq = 0;
+    cub::DeviceSelect::Unique(nullptr, unq, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int*)nullptr, (int)g3);
+    if (unq > sel) sel = unq;
     return al256(sel > srt ? sel : srt);
 }
 struct GridWs {
     float* tmp; uint8_t* flags; int* occ_list; int* occ_count; int* cell_idx; float* xyz; float* sigma; float* stats;
+    int* tot;  // [0..C]: first slot of each cascade / total; [63]: number of distinct keys of the cascade being picked
     uint32_t* keys; uint32_t* keys_sorted; void* cub_temp; size_t cub_bytes; size_t total;
 };
 static GridWs grid_ws(void* workspace, int cascades, size_t g3) {
@@ -1304,6 +1315,7 @@ static GridWs grid_ws(void* workspace, int cascades, size_t g3) {
     g.xyz = (float*)w; w += al256(C * g3 * 12);
     g.sigma = (float*)w; w += al256(C * g3 * 4);
     g.stats = (float*)w; w += 256;
+    g.tot = (int*)w; w += 256;
     g.keys = (uint32_t*)w; w += al256(g3 * 4);
     g.keys_sorted = (uint32_t*)w; w += al256(g3 * 4);
     g.cub_temp = w;
@@ -1322,7 +1334,8 @@ extern "C" size_t ngp_update_grid_workspace(int cascades, int grid_size) {
 extern "C" int ngp_update_density_grid_pick(const float* density_grid, int cascades, int grid_size, float scale,
                                             float density_threshold, int warmup, uint32_t seed, void* workspace,
                                             size_t workspace_bytes, void* stream) {
-    if (!density_grid || !workspace || cascades < 1 || grid_size < 2 || grid_size > 1024) return NGP_EINVAL;
+    if (!density_grid || !workspace || cascades < 1 || cascades > 62 || grid_size < 2 || grid_size > 1024) return NGP_EINVAL;
+    if ((int64_t)cascades * grid_size * grid_size * grid_size > 0x7fffffffll) return NGP_EINVAL;  // cell_idx = c * g3 + cell
     if (workspace_bytes < ngp_update_grid_workspace(cascades, grid_size)) return NGP_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t g3 = (size_t)grid_size * grid_size * grid_size;
@@ -1336,6 +1349,8 @@ extern "C" int ngp_update_density_grid_pick(const float* density_grid, int casca
     NGP_COUNT_LAUNCHES(2);
     NGP_TRACE(20, st);
     const uint32_t n_slots = warmup ? (uint32_t)g3 : 2u * u.M;
+    NGP_CUDA(cudaMemsetAsync(g.tot, 0, 256, st));
+    NGP_COUNT_LAUNCHES(1);
     for (int c = 0; c < cascades; ++c) {
         if (!warmup) {
             k_grid_flags<<<ngp_div_up(g3, 256), 256, 0, st>>>(density_grid + c * g3, (int64_t)g3, density_threshold, g.flags);
@@ -1349,9 +1364,12 @@ extern "C" int ngp_update_density_grid_pick(const float* density_grid, int casca
             NGP_CUDA(cub::DeviceRadixSort::SortKeys(g.cub_temp, cub_bytes, (const uint32_t*)g.keys, g.keys_sorted, (int)n_slots,
                                                     0, key_bits(g3), st));
             NGP_COUNT_LAUNCHES(2 + (key_bits(g3) + 7) / 8);  // cub onesweep: histogram + scan + one kernel per 8-bit digit
+            NGP_CUDA(cub::DeviceSelect::Unique(g.cub_temp, cub_bytes, (const uint32_t*)g.keys_sorted, g.keys, g.tot + 63,
+                                               (int)n_slots, st));
+            NGP_COUNT_LAUNCHES(2);
         }
-        k_grid_jitter<<<ngp_div_up(n_slots, 256), 256, 0, st>>>(u, c, warmup ? nullptr : g.keys_sorted,
-                                                                g.cell_idx + (size_t)c * n_slots, g.xyz + 3 * (size_t)c * n_slots);
+        k_grid_jitter<<<ngp_div_up(n_slots, 256), 256, 0, st>>>(u, c, warmup ? nullptr : g.keys, g.tot + 63, g.tot, g.cell_idx,
+                                                                g.xyz);
         NGP_CHECK_LAUNCH();
         NGP_TRACE(22, st);
     }
@@ -1369,14 +1387,15 @@ extern "C" int ngp_update_density_grid_eval(const NgpNet* net, float* density_gr
     const size_t g3 = (size_t)grid_size * grid_size * grid_size;
     const GridWs g = grid_ws(workspace, cascades, g3);
     const size_t n_slots = warmup ? g3 : 2 * (g3 / 4);
-    const size_t n_all = n_slots * (size_t)cascades;
+    const size_t n_all = n_slots * (size_t)cascades;  // capacity; the regular refresh evaluates tot[cascades] distinct cells
     NgpSamples smp;
     smp.xyzs = g.xyz; smp.dirs = nullptr; smp.rays_o = nullptr; smp.rays_d = nullptr; smp.ray_idx = nullptr; smp.ts = nullptr;
-    smp.n = (int64_t)n_all; smp.n_dev = nullptr; smp.live_idx = nullptr; smp.n_live_dev = nullptr;
+    smp.n = (int64_t)n_all; smp.n_dev = warmup ? nullptr : g.tot + cascades; smp.live_idx = nullptr; smp.n_live_dev = nullptr;
     int rc = ngp_net_forward(net, &smp, 0, g.sigma, nullptr, nullptr, nullptr, stream);
     if (rc) return rc;
-    k_grid_scatter<<<ngp_div_up(n_all, 256), 256, 0, st>>>(g.cell_idx, g.sigma, (uint32_t)n_slots, (uint32_t)n_all, (uint32_t)g3,
-                                                           g.tmp);
+    int sgrid = ngp_div_up(n_all, 256);
+    if (sgrid > ngp_sm_count() * 16) sgrid = ngp_sm_count() * 16;
+    k_grid_scatter<<<sgrid, 256, 0, st>>>(g.cell_idx, g.sigma, smp.n_dev, (uint32_t)n_all, g.tmp);
     NGP_CHECK_LAUNCH();
     NGP_TRACE(23, st);
     int grid = ngp_div_up((int64_t)cascades * g3, 256);
