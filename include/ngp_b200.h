@@ -212,8 +212,9 @@ int ngp_grad_scale(const float* dL_dsigmas, const float* sigmas, const float* dL
 
 /* ----------------------------------------------------------------------------------------------
  * Fused training path: the body of render(..., test_time=False) (reference models/rendering.py:11-43,
- * :121-163) without a single host synchronisation -- AABB + near clamp + march (one pass, per-ray
- * staging) -> prefix sum -> compaction -> ngp_net_forward -> ragged compositing, and its backward.
+ * :121-163) without a single host synchronisation -- AABB + near clamp + march + segment allocation (one
+ * kernel: per-ray staging, one atomicAdd per ray hands out its segment, coalesced copy-out) -> ngp_net_forward ->
+ * ragged compositing, and its backward.
  * All sample counts stay on the device; every per-sample buffer is sized for `max_total_samples`
  * (n_rays * max_samples can never overflow).
  * -------------------------------------------------------------------------------------------- */
@@ -272,7 +273,7 @@ size_t ngp_train_scan_temp_bytes(int n_rays); /* NgpTrainBuffers.scan_temp size;
 /* forward = __render_rays_train (models/rendering.py:121-163) incl. the AABB test and near clamp of render() (:25-29):
  * fills per-ray rgb/opacity/depth (+ws) and everything the backward needs */
 int ngp_render_train_fwd(const NgpNet* net, const NgpTrainCfg* cfg, const NgpTrainBuffers* buf, void* stream);
-/* its two halves: _march (AABB + march + scan + compaction; independent of the weights, so it may overlap the
+/* its two halves: _march (AABB + march + segment allocation + copy-out; independent of the weights, so it may overlap the
  * optimiser of the previous step) and _net (network + compositing). _fwd == _march then _net. */
 int ngp_render_train_march(const NgpTrainCfg* cfg, const NgpTrainBuffers* buf, void* stream);
 int ngp_render_train_net(const NgpNet* net, const NgpTrainCfg* cfg, const NgpTrainBuffers* buf, void* stream);

@@ -450,7 +450,7 @@ class Trainer:
         self._staged = nxt
 
     def march(self, jitter=True):
-        """first half of the forward: start jitter + AABB + march + scan + compaction (independent of the weights)"""
+        """first half of the forward: start jitter + AABB + march + segment allocation (independent of the weights)"""
         if jitter:
             self.noise.uniform_(0, 1, generator=self.gen)
         if self.random_bg:
@@ -607,7 +607,7 @@ class Trainer:
 
     def capture(self, sample=True):
         """Record the step into CUDA graphs, one [prepare, compute] pair per buffer set plus the optimiser:
-            g_prepare[i]    = [device RNG, ngp_gen_rays, march, scan, compaction]          -> writes set i
+            g_prepare[i]    = [batch assembly (k_sample_rays), AABB + march + segment allocation]   -> writes set i
             g_compute[i][b] = [network fwd, compositing, NeRFLoss, compositing bwd, loss scale, MLP bwd, scatter]
                               reads set i, accumulates into gradient buffer b
             g_update[b]     = [Adam], or for N > 1 the self-synchronising exchange kernel reducing buffer b and clearing
