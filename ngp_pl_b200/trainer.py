@@ -403,6 +403,7 @@ class Trainer:
                 done = torch.cuda.Event()
                 done.record(main)
                 self._pick_stream.wait_event(done)
+                m.density_grid.record_stream(self._pick_stream)  # read there: keep its memory from being recycled under the pick
                 self._launch_pick(nxt, density_threshold, warm_next, self._pick_stream)
                 ev = torch.cuda.Event()
                 ev.record(self._pick_stream)
